@@ -1,0 +1,1682 @@
+/*
+ * lgpu_api.cu -- C ABI implementation of liblorads_b200.so (declared in include/lorads_b200.h).
+ *
+ * Host side of the device layer: problem preprocessing (the reference's AConeProcData /
+ * AConePresolveData rules re-derived for a uniform device layout), device memory, kernel
+ * sequencing per reference function.  Control flow of the solver (ALM/ADMM state machines,
+ * line-search root selection, printing) stays in the C host driver (csrc/host/).
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/lorads_b200.h"
+#include "lgpu_kernels.cuh"
+
+/* ------------------------------------------------------------------------------------------------
+ * error handling
+ * ------------------------------------------------------------------------------------------------*/
+#define LGPU_FAIL(ctx, ...)                                   \
+    do {                                                      \
+        char _buf[512];                                       \
+        snprintf(_buf, sizeof(_buf), __VA_ARGS__);            \
+        (ctx)->err = _buf;                                    \
+        return 1;                                             \
+    } while (0)
+
+#define CU(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) LGPU_FAIL(ctx, "%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define CHECK_LAUNCH(ctx)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                               \
+        if (_e != cudaSuccess) LGPU_FAIL(ctx, "%s:%d kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define TRY(x)              \
+    do {                    \
+        int _rc = (x);      \
+        if (_rc) return _rc; \
+    } while (0)
+
+static thread_local std::string g_create_err;
+
+template <class T>
+static int dev_alloc(lgpu_ctx *ctx, T **p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU(ctx, cudaMalloc((void **)p, count * sizeof(T)));
+    return 0;
+}
+template <class T>
+static int dev_upload(lgpu_ctx *ctx, T **p, const std::vector<T> &h)
+{
+    TRY(dev_alloc(ctx, p, h.size()));
+    if (!h.empty()) CU(ctx, cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+template <class T>
+static void dev_free(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * launch helpers
+ * ------------------------------------------------------------------------------------------------*/
+static inline int grid_for(const lgpu_ctx *ctx, int64_t threads_needed)
+{
+    int64_t blocks = (threads_needed + LGPU_TPB - 1) / LGPU_TPB;
+    int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (cap > LGPU_MAX_PARTIAL_BLOCKS) cap = LGPU_MAX_PARTIAL_BLOCKS;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <class F>
+static void launch_map(lgpu_ctx *ctx, int64_t n, F f)
+{
+    if (n <= 0) return;
+    k_map<<<grid_for(ctx, n), LGPU_TPB, 0, ctx->stream>>>(n, f);
+    ctx->launches++;
+}
+template <int K, class F>
+static void launch_reduce(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec)
+{
+    k_reduce<K><<<grid_for(ctx, n > 0 ? n : 1), LGPU_TPB, 0, ctx->stream>>>(n, f, ctx->partials, ctx->counter, ctx->dsc, spec);
+    ctx->launches++;
+}
+template <class F>
+static void launch_scalar(lgpu_ctx *ctx, F f)
+{
+    k_scalar<<<1, 32, 0, ctx->stream>>>(f);
+    ctx->launches++;
+}
+static SlotSpec<1> slot1(int s, int acc = 0)
+{
+    SlotSpec<1> sp;
+    sp.slot[0] = s;
+    sp.accumulate = acc;
+    return sp;
+}
+
+static int fetch_scalars(lgpu_ctx *ctx, int first, int count)
+{
+    CU(ctx, cudaMemcpyAsync(ctx->hsc + first, ctx->dsc + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static inline int pick_group(int64_t ld)
+{
+    const int64_t words = ld / 2;
+    if (words <= 4) return 4;
+    if (words <= 8) return 8;
+    if (words <= 16) return 16;
+    return 32;
+}
+static inline int pick_list_group(double avg_len)
+{
+    if (avg_len <= 2.0) return 1;
+    if (avg_len <= 12.0) return 4;
+    return 32;
+}
+
+#define DISPATCH_G(G, ...)              \
+    switch (G) {                        \
+    case 1: { constexpr int GG = 1; __VA_ARGS__; } break;   \
+    case 4: { constexpr int GG = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int GG = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int GG = 16; __VA_ARGS__; } break; \
+    default: { constexpr int GG = 32; __VA_ARGS__; } break; \
+    }
+
+/* UVt on the pattern of cone c from two row-major factors */
+static void run_uvt(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *U, const double *V, double *out)
+{
+    const int G = pick_group(ld);
+    const int same = (U == V) ? 1 : 0;
+    DISPATCH_G(G, k_uvt<GG><<<grid_for(ctx, c.nnzP * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.nnzP, c.pat_row, c.pat_col, U, V, (int)ld, same, out));
+    ctx->launches++;
+}
+/* cv = A_c(uvt) (compact, per non-zero constraint) */
+static void run_con_gather(lgpu_ctx *ctx, DevCone &c, const double *uvt, double *cv)
+{
+    if (c.mA == 0) return;
+    const int G = pick_list_group((double)c.nnzA / (double)c.mA);
+    DISPATCH_G(G, k_con_gather<GG><<<grid_for(ctx, c.mA * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.mA, c.a_ptr, c.a_slot, c.a_coef, uvt, cv));
+    ctx->launches++;
+}
+/* <C, uvt> accumulated into dsc[slot] */
+static void run_obj_gather(lgpu_ctx *ctx, DevCone &c, const double *uvt, int slot, int accumulate)
+{
+    const int32_t *cs = c.c_slot;
+    const double *cc = c.c_coef;
+    launch_reduce<1>(ctx, c.nnzC, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(cc[i], uvt[cs[i]], acc[0]); },
+                     slot1(slot, accumulate));
+}
+/* S = [C] + sum w A ; w indexed by global id (w_global) or compact id */
+static void run_wsum(lgpu_ctx *ctx, DevCone &c, const double *w, bool w_global, bool add_obj, double wscale, double *S)
+{
+    const int G = pick_list_group(c.nnzP > 0 ? (double)c.nnzA / (double)c.nnzP : 0.0);
+    const int32_t *tidx = w_global ? c.t_gid : c.t_loc;
+    DISPATCH_G(G, k_wsum<GG><<<grid_for(ctx, c.nnzP * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.nnzP, c.t_ptr, tidx, c.t_val, w, c.cval, add_obj ? 1 : 0, wscale, S));
+    ctx->launches++;
+}
+/* Y = alpha S X + beta Z */
+static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, const double *X, double alpha, double beta,
+                     const double *Z, double *Y)
+{
+    const int G = pick_group(ld);
+    DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.n, c.f_ptr, c.f_col, c.f_slot, S, X, (int)ld, alpha, beta, Z, Y));
+    ctx->launches++;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * lifecycle
+ * ------------------------------------------------------------------------------------------------*/
+extern "C" const char *lgpu_version(void) { return "lorads_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *lgpu_last_error(const lgpu_ctx *ctx)
+{
+    if (!ctx) return g_create_err.c_str();
+    return ctx->err.c_str();
+}
+extern "C" int64_t lgpu_launch_count(const lgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int lgpu_create(lgpu_ctx **out, int device)
+{
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                       " (liblorads_b200 has no CPU fallback)";
+        return 1;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_err = "device index out of range";
+        return 1;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    lgpu_ctx *ctx = new lgpu_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->dsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->hsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->partials, sizeof(double) * 8 * LGPU_MAX_PARTIAL_BLOCKS) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->counter, sizeof(unsigned int)) != cudaSuccess) {
+        g_create_err = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return 1;
+    }
+    cudaMemsetAsync(ctx->dsc, 0, sizeof(double) * LGPU_NSCALAR, ctx->stream);
+    cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream);
+    memset(ctx->hsc, 0, sizeof(double) * LGPU_NSCALAR);
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return 0;
+}
+
+static void free_cone(DevCone &c)
+{
+    dev_free(c.pat_row); dev_free(c.pat_col); dev_free(c.cval); dev_free(c.c_slot); dev_free(c.c_coef);
+    dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid);
+    dev_free(c.t_ptr); dev_free(c.t_loc); dev_free(c.t_gid); dev_free(c.t_val);
+    dev_free(c.f_ptr); dev_free(c.f_col); dev_free(c.f_slot); dev_free(c.d_row); dev_free(c.d_val);
+    dev_free(c.uvt); dev_free(c.S); dev_free(c.cv); dev_free(c.wtmp);
+}
+static void free_vars(lgpu_ctx *ctx)
+{
+    dev_free(ctx->R); dev_free(ctx->U); dev_free(ctx->V); dev_free(ctx->G); dev_free(ctx->M2); dev_free(ctx->bLin);
+    dev_free(ctx->cg_r); dev_free(ctx->cg_p); dev_free(ctx->cg_Q); dev_free(ctx->stage);
+    for (auto &p : ctx->s) dev_free(p);
+    for (auto &p : ctx->y) dev_free(p);
+    ctx->s.clear();
+    ctx->y.clear();
+    ctx->vars_ready = false;
+}
+
+extern "C" void lgpu_destroy(lgpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &c : ctx->cones) free_cone(c);
+    free_vars(ctx);
+    dev_free(ctx->b); dev_free(ctx->lam); dev_free(ctx->cvs); dev_free(ctx->q1); dev_free(ctx->q2); dev_free(ctx->M1);
+    dev_free(ctx->mtmp);
+    dev_free(ctx->lp.obj); dev_free(ctx->lp.r_ptr); dev_free(ctx->lp.r_col); dev_free(ctx->lp.r_val);
+    dev_free(ctx->lp.c_ptr); dev_free(ctx->lp.c_row); dev_free(ctx->lp.c_val); dev_free(ctx->lp.nrm2sq);
+    dev_free(ctx->dsc); dev_free(ctx->partials); dev_free(ctx->counter);
+    if (ctx->hsc) cudaFreeHost(ctx->hsc);
+    if (ctx->hstage) cudaFreeHost(ctx->hstage);
+    if (ctx->dstage) cudaFree(ctx->dstage);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static int ensure_stage(lgpu_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->hstage_bytes) {
+        if (ctx->hstage) cudaFreeHost(ctx->hstage);
+        ctx->hstage = nullptr;
+        ctx->hstage_bytes = 0;
+        CU(ctx, cudaMallocHost((void **)&ctx->hstage, bytes));
+        ctx->hstage_bytes = bytes;
+    }
+    if (bytes > ctx->dstage_bytes) {
+        if (ctx->dstage) cudaFree(ctx->dstage);
+        ctx->dstage = nullptr;
+        ctx->dstage_bytes = 0;
+        CU(ctx, cudaMalloc(&ctx->dstage, bytes));
+        ctx->dstage_bytes = bytes;
+    }
+    return 0;
+}
+
+static int ensure_dstage(lgpu_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->dstage_bytes) {
+        if (ctx->dstage) cudaFree(ctx->dstage);
+        ctx->dstage = nullptr;
+        ctx->dstage_bytes = 0;
+        CU(ctx, cudaMalloc(&ctx->dstage, bytes));
+        ctx->dstage_bytes = bytes;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * problem upload
+ * ------------------------------------------------------------------------------------------------*/
+extern "C" int lgpu_set_problem(lgpu_ctx *ctx, int64_t m, const double *b, int n_cones, const int64_t *blk_dims,
+                                int64_t n_lp_cols)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (m <= 0 || n_cones < 0 || m >= (int64_t)1 << 31) LGPU_FAIL(ctx, "bad problem sizes");
+    for (auto &c : ctx->cones) free_cone(c);
+    ctx->cones.clear();
+    ctx->cones.resize(n_cones);
+    ctx->m = m;
+    ctx->ncones = n_cones;
+    for (int c = 0; c < n_cones; ++c) {
+        if (blk_dims[c] <= 0 || blk_dims[c] >= (int64_t)1 << 31) LGPU_FAIL(ctx, "bad block dimension");
+        ctx->cones[c].n = blk_dims[c];
+    }
+    ctx->lp = DevLp();
+    ctx->lp.n = n_lp_cols;
+    ctx->h_b.assign(b, b + m);
+    dev_free(ctx->b); dev_free(ctx->lam); dev_free(ctx->cvs); dev_free(ctx->q1); dev_free(ctx->q2); dev_free(ctx->M1);
+    dev_free(ctx->mtmp);
+    TRY(dev_upload(ctx, &ctx->b, ctx->h_b));
+    double **mv[] = {&ctx->lam, &ctx->cvs, &ctx->q1, &ctx->q2, &ctx->M1, &ctx->mtmp};
+    for (auto p : mv) {
+        TRY(dev_alloc(ctx, p, (size_t)m));
+        CU(ctx, cudaMemsetAsync(*p, 0, sizeof(double) * m, ctx->stream));
+    }
+    /* |b| norms.  Quirk Q2 (lorads_solver.c:1468-1472): the reference indexes b with the 1-based result of
+     * idamax_, i.e. it reads the element AFTER the first maximum; one past the end reads a heap word that is
+     * never a meaningful double (treated as 0 here). */
+    double n1 = 0, n2 = 0, mx = -1;
+    int64_t imax = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        n1 += fabs(b[i]);
+        n2 += b[i] * b[i];
+        if (fabs(b[i]) > mx) { mx = fabs(b[i]); imax = i; }
+    }
+    ctx->b_nrm1 = n1;
+    ctx->b_nrm2 = sqrt(n2);
+    ctx->b_nrminf_q = (imax + 1 < m) ? fabs(b[imax + 1]) : 0.0;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static inline void unpack_lower(int64_t n, int64_t idx, int64_t *row, int64_t *col)
+{
+    /* column-major packed lower triangle: start(j) = j (2n - j + 1) / 2  (PACK_IDX, lorads_utils.h:167) */
+    double t = (2.0 * (double)n + 1.0);
+    int64_t j = (int64_t)floor((t - sqrt(t * t - 8.0 * (double)idx)) / 2.0);
+    if (j < 0) j = 0;
+    if (j > n - 1) j = n - 1;
+    while (j > 0 && j * (2 * n - j + 1) / 2 > idx) --j;
+    while (j + 1 < n && (j + 1) * (2 * n - j) / 2 <= idx) ++j;
+    *col = j;
+    *row = idx - j * (2 * n - j + 1) / 2 + j;
+}
+
+extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, const int64_t *idx_in, const double *val_in)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    const int64_t n = c.n, m = ctx->m;
+    const int64_t tri = n * (n + 1) / 2;
+    const int64_t total = beg[m + 1];
+    /* per-column ascending order (dataMatCreateSparseImpl sorts when needed, lorads_sdp_data.c:100-102) */
+    std::vector<int64_t> idx(idx_in, idx_in + total);
+    std::vector<double> val(val_in, val_in + total);
+    for (int64_t col = 0; col <= m; ++col) {
+        const int64_t e0 = beg[col], e1 = beg[col + 1];
+        bool asc = true;
+        for (int64_t e = e0 + 1; e < e1; ++e)
+            if (idx[e] < idx[e - 1]) { asc = false; break; }
+        if (!asc) {
+            std::vector<int64_t> o(e1 - e0);
+            std::iota(o.begin(), o.end(), (int64_t)0);
+            std::stable_sort(o.begin(), o.end(), [&](int64_t a, int64_t b2) { return idx[e0 + a] < idx[e0 + b2]; });
+            std::vector<int64_t> ti(e1 - e0);
+            std::vector<double> tv(e1 - e0);
+            for (size_t q = 0; q < o.size(); ++q) { ti[q] = idx[e0 + o[q]]; tv[q] = val[e0 + o[q]]; }
+            std::copy(ti.begin(), ti.end(), idx.begin() + e0);
+            std::copy(tv.begin(), tv.end(), val.begin() + e0);
+        }
+    }
+    /* storage classes (sdpDataMatSetData, lorads_sdp_data.c:1180-1197) */
+    auto mtype = [&](int64_t nnz) -> int {
+        if (nnz == 0) return 0;
+        if ((double)nnz > 0.1 * (double)tri) return 2;
+        return 1;
+    };
+    c.obj_type = mtype(beg[1] - beg[0]);
+    bool any_dense = c.obj_type == 2;
+    int64_t mA = 0;
+    for (int64_t col = 1; col <= m; ++col) {
+        const int64_t nnz = beg[col + 1] - beg[col];
+        if (nnz > 0) ++mA;
+        if (mtype(nnz) == 2) any_dense = true;
+    }
+    c.mA = mA;
+    c.sparse_container = !((double)mA > 0.3 * (double)m); /* LUserDataChooseCone, lorads_user_data.c:105-109 */
+    /* aggregate: dense if n < 20, any dense member, or |union| >= 10% of the triangle (AConePresolveData) */
+    bool dense = (n < 20) || any_dense;
+    std::vector<int64_t> pat;
+    if (!dense) {
+        pat = idx;
+        std::sort(pat.begin(), pat.end());
+        pat.erase(std::unique(pat.begin(), pat.end()), pat.end());
+        if ((double)pat.size() / (double)tri >= 0.1) dense = true;
+    }
+    c.dense_aggregate = dense;
+    if (dense) {
+        if (tri >= (int64_t)1 << 30) LGPU_FAIL(ctx, "dense aggregate too large for this build (n=%lld)", (long long)n);
+        pat.resize(tri);
+        std::iota(pat.begin(), pat.end(), (int64_t)0);
+    }
+    const int64_t nnzP = (int64_t)pat.size();
+    if (nnzP >= (int64_t)1 << 31 || total >= (int64_t)1 << 31) LGPU_FAIL(ctx, "cone too large for 32-bit device indices");
+    c.nnzP = nnzP;
+    c.h_pat_row.resize(nnzP);
+    c.h_pat_col.resize(nnzP);
+    int64_t ndiag = 0;
+    for (int64_t k = 0; k < nnzP; ++k) {
+        int64_t r, q;
+        unpack_lower(n, pat[k], &r, &q);
+        c.h_pat_row[k] = (int32_t)r;
+        c.h_pat_col[k] = (int32_t)q;
+        if (r == q) ++ndiag;
+    }
+    auto slot_of = [&](int64_t packed) -> int32_t {
+        if (dense) return (int32_t)packed;
+        return (int32_t)(std::lower_bound(pat.begin(), pat.end(), packed) - pat.begin());
+    };
+    /* objective */
+    std::vector<double> cval(nnzP, 0.0), c_coef;
+    std::vector<int32_t> c_slot;
+    c.c_nrm1 = c.c_nrm2sq = c.c_nrminf = 0.0;
+    for (int64_t e = beg[0]; e < beg[1]; ++e) {
+        const int32_t s = slot_of(idx[e]);
+        const bool dg = c.h_pat_row[s] == c.h_pat_col[s];
+        cval[s] += val[e];
+        c_slot.push_back(s);
+        c_coef.push_back(dg ? val[e] : 2.0 * val[e]);
+        c.c_nrm1 += (dg ? 1.0 : 2.0) * fabs(val[e]);
+        c.c_nrm2sq += (dg ? 1.0 : 2.0) * val[e] * val[e];
+        c.c_nrminf = std::max(c.c_nrminf, fabs(val[e]));
+    }
+    c.nnzC = (int64_t)c_slot.size();
+    /* constraints: CSR over non-zero constraints */
+    std::vector<int32_t> a_ptr(1, 0), a_slot, con_gid;
+    std::vector<double> a_coef, a_raw;
+    a_slot.reserve(total);
+    a_coef.reserve(total);
+    a_raw.reserve(total);
+    bool diag_only = mA > 0;
+    std::vector<int32_t> d_row;
+    std::vector<double> d_val;
+    c.max_con_len = 0;
+    for (int64_t col = 1; col <= m; ++col) {
+        const int64_t e0 = beg[col], e1 = beg[col + 1];
+        if (e1 == e0) continue;
+        con_gid.push_back((int32_t)(col - 1));
+        for (int64_t e = e0; e < e1; ++e) {
+            const int32_t s = slot_of(idx[e]);
+            const bool dg = c.h_pat_row[s] == c.h_pat_col[s];
+            a_slot.push_back(s);
+            a_raw.push_back(val[e]);
+            a_coef.push_back(dg ? val[e] : 2.0 * val[e]);
+            if (!dg) diag_only = false;
+        }
+        if (e1 - e0 != 1) diag_only = false;
+        else if (diag_only) { d_row.push_back(c.h_pat_row[a_slot.back()]); d_val.push_back(val[e0]); }
+        c.max_con_len = std::max<int64_t>(c.max_con_len, e1 - e0);
+        a_ptr.push_back((int32_t)a_slot.size());
+    }
+    c.nnzA = (int64_t)a_slot.size();
+    c.diag_only = diag_only;
+    /* transpose by slot: counting sort, stable in constraint order (the reference's accumulation order) */
+    std::vector<int32_t> t_ptr(nnzP + 1, 0), t_loc(c.nnzA), t_gid(c.nnzA);
+    std::vector<double> t_val(c.nnzA);
+    for (int64_t e = 0; e < c.nnzA; ++e) t_ptr[a_slot[e] + 1]++;
+    c.max_slot_len = 0;
+    for (int64_t k = 0; k < nnzP; ++k) {
+        c.max_slot_len = std::max<int64_t>(c.max_slot_len, t_ptr[k + 1]);
+        t_ptr[k + 1] += t_ptr[k];
+    }
+    {
+        std::vector<int32_t> fill(t_ptr.begin(), t_ptr.end() - 1);
+        for (int64_t t = 0; t < mA; ++t)
+            for (int32_t e = a_ptr[t]; e < a_ptr[t + 1]; ++e) {
+                const int32_t p = fill[a_slot[e]]++;
+                t_loc[p] = (int32_t)t;
+                t_gid[p] = con_gid[t];
+                t_val[p] = a_raw[e];
+            }
+    }
+    /* full symmetric CSR: row -> (col, slot) */
+    c.nnzF = 2 * nnzP - ndiag;
+    if (c.nnzF >= (int64_t)1 << 31) LGPU_FAIL(ctx, "cone too large for 32-bit device indices");
+    std::vector<int32_t> f_ptr(n + 1, 0), f_col(c.nnzF), f_slot(c.nnzF);
+    for (int64_t k = 0; k < nnzP; ++k) {
+        f_ptr[c.h_pat_row[k] + 1]++;
+        if (c.h_pat_row[k] != c.h_pat_col[k]) f_ptr[c.h_pat_col[k] + 1]++;
+    }
+    for (int64_t i = 0; i < n; ++i) f_ptr[i + 1] += f_ptr[i];
+    {
+        /* pattern is sorted by (col,row): emitting the (col -> row) entries first in k order and the
+         * (row -> col) ones in a second pass keeps every CSR row sorted by column */
+        std::vector<int32_t> fill(f_ptr.begin(), f_ptr.end() - 1);
+        /* entries (i, j) with j < i come from pattern entries with col=j: ascending k visits ascending j */
+        for (int64_t k = 0; k < nnzP; ++k) {
+            const int32_t i = c.h_pat_row[k], j = c.h_pat_col[k];
+            const int32_t p = fill[i]++;
+            f_col[p] = j;
+            f_slot[p] = (int32_t)k;
+        }
+        for (int64_t k = 0; k < nnzP; ++k) {
+            const int32_t i = c.h_pat_row[k], j = c.h_pat_col[k];
+            if (i == j) continue;
+            const int32_t p = fill[j]++;
+            f_col[p] = i;
+            f_slot[p] = (int32_t)k;
+        }
+    }
+    /* upload */
+    free_cone(c);
+    TRY(dev_upload(ctx, &c.pat_row, c.h_pat_row));
+    TRY(dev_upload(ctx, &c.pat_col, c.h_pat_col));
+    TRY(dev_upload(ctx, &c.cval, cval));
+    TRY(dev_upload(ctx, &c.c_slot, c_slot));
+    TRY(dev_upload(ctx, &c.c_coef, c_coef));
+    TRY(dev_upload(ctx, &c.a_ptr, a_ptr));
+    TRY(dev_upload(ctx, &c.a_slot, a_slot));
+    TRY(dev_upload(ctx, &c.a_coef, a_coef));
+    TRY(dev_upload(ctx, &c.con_gid, con_gid));
+    TRY(dev_upload(ctx, &c.t_ptr, t_ptr));
+    TRY(dev_upload(ctx, &c.t_loc, t_loc));
+    TRY(dev_upload(ctx, &c.t_gid, t_gid));
+    TRY(dev_upload(ctx, &c.t_val, t_val));
+    TRY(dev_upload(ctx, &c.f_ptr, f_ptr));
+    TRY(dev_upload(ctx, &c.f_col, f_col));
+    TRY(dev_upload(ctx, &c.f_slot, f_slot));
+    if (diag_only) {
+        TRY(dev_upload(ctx, &c.d_row, d_row));
+        TRY(dev_upload(ctx, &c.d_val, d_val));
+    }
+    TRY(dev_alloc(ctx, &c.uvt, (size_t)nnzP));
+    TRY(dev_alloc(ctx, &c.S, (size_t)nnzP));
+    TRY(dev_alloc(ctx, &c.cv, (size_t)std::max<int64_t>(mA, 1)));
+    TRY(dev_alloc(ctx, &c.wtmp, (size_t)std::max<int64_t>(mA, 1)));
+    CU(ctx, cudaMemsetAsync(c.cv, 0, sizeof(double) * std::max<int64_t>(mA, 1), ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lgpu_lp_upload(lgpu_ctx *ctx, const int64_t *beg, const int64_t *idx, const double *val)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevLp &lp = ctx->lp;
+    const int64_t m = ctx->m, n = lp.n;
+    if (n <= 0) LGPU_FAIL(ctx, "no LP block declared in lgpu_set_problem");
+    lp.h_obj.assign(n, 0.0);
+    for (int64_t e = beg[0]; e < beg[1]; ++e) lp.h_obj[idx[e]] = val[e]; /* lorads_lp_conic.c:38-40 */
+    std::vector<int32_t> r_ptr(m + 1, 0), r_col;
+    std::vector<double> r_val;
+    std::vector<int64_t> cnt(n, 0);
+    for (int64_t i = 0; i < m; ++i) {
+        for (int64_t e = beg[i + 1]; e < beg[i + 2]; ++e) {
+            r_col.push_back((int32_t)idx[e]);
+            r_val.push_back(val[e]);
+            cnt[idx[e]]++;
+        }
+        r_ptr[i + 1] = (int32_t)r_col.size();
+    }
+    lp.nnz = (int64_t)r_col.size();
+    lp.h_c_ptr.assign(n + 1, 0);
+    for (int64_t j = 0; j < n; ++j) lp.h_c_ptr[j + 1] = lp.h_c_ptr[j] + (int32_t)cnt[j];
+    lp.h_c_row.resize(lp.nnz);
+    lp.h_c_val.resize(lp.nnz);
+    {
+        std::vector<int32_t> fill(lp.h_c_ptr.begin(), lp.h_c_ptr.end() - 1);
+        for (int64_t i = 0; i < m; ++i)
+            for (int32_t e = r_ptr[i]; e < r_ptr[i + 1]; ++e) {
+                const int32_t p = fill[r_col[e]]++;
+                lp.h_c_row[p] = (int32_t)i;
+                lp.h_c_val[p] = r_val[e];
+            }
+    }
+    lp.h_nrm2sq.assign(n, 0.0);
+    for (int64_t j = 0; j < n; ++j) {
+        double s = 0;
+        for (int32_t e = lp.h_c_ptr[j]; e < lp.h_c_ptr[j + 1]; ++e) s += lp.h_c_val[e] * lp.h_c_val[e];
+        const double t = sqrt(s); /* nrm2 then squared, lorads_lp_conic.c:112-113 */
+        lp.h_nrm2sq[j] = t * t;
+        if (lp.h_c_ptr[j + 1] == lp.h_c_ptr[j]) LGPU_FAIL(ctx, "LP column %lld has no constraint entry (the reference rejects it too)", (long long)j);
+    }
+    /* norms, with the reference's quirks (lorads_lp_conic.c:170-196): |c|_2^2 := |c|_1^2, |c|_inf off by one */
+    double n1 = 0, mx = -1;
+    int64_t imax = 0;
+    for (int64_t j = 0; j < n; ++j) {
+        n1 += fabs(lp.h_obj[j]);
+        if (fabs(lp.h_obj[j]) > mx) { mx = fabs(lp.h_obj[j]); imax = j; }
+    }
+    lp.nrm1 = n1;
+    lp.nrminf_q = (imax + 1 < n) ? fabs(lp.h_obj[imax + 1]) : 0.0;
+    dev_free(lp.obj); dev_free(lp.r_ptr); dev_free(lp.r_col); dev_free(lp.r_val);
+    dev_free(lp.c_ptr); dev_free(lp.c_row); dev_free(lp.c_val); dev_free(lp.nrm2sq);
+    TRY(dev_upload(ctx, &lp.obj, lp.h_obj));
+    TRY(dev_upload(ctx, &lp.r_ptr, r_ptr));
+    TRY(dev_upload(ctx, &lp.r_col, r_col));
+    TRY(dev_upload(ctx, &lp.r_val, r_val));
+    TRY(dev_upload(ctx, &lp.c_ptr, lp.h_c_ptr));
+    TRY(dev_upload(ctx, &lp.c_row, lp.h_c_row));
+    TRY(dev_upload(ctx, &lp.c_val, lp.h_c_val));
+    TRY(dev_upload(ctx, &lp.nrm2sq, lp.h_nrm2sq));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lgpu_cone_info(const lgpu_ctx *ctx, int cone, int64_t out[6])
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    const DevCone &c = ctx->cones[cone];
+    out[0] = c.mA;
+    out[1] = c.dense_aggregate ? 1 : 0;
+    out[2] = c.sparse_container ? 1 : 0;
+    out[3] = c.nnzP;
+    out[4] = c.diag_only ? 1 : 0;
+    out[5] = c.nnzA;
+    return 0;
+}
+
+extern "C" int lgpu_cone_pattern(const lgpu_ctx *ctx, int cone, int64_t cap, int32_t *row, int32_t *col)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    const DevCone &c = ctx->cones[cone];
+    const int64_t k = std::min<int64_t>(cap, c.nnzP);
+    memcpy(row, c.h_pat_row.data(), sizeof(int32_t) * k);
+    memcpy(col, c.h_pat_col.data(), sizeof(int32_t) * k);
+    return 0;
+}
+
+extern "C" int lgpu_constants(const lgpu_ctx *ctx, double out[6])
+{
+    if (!ctx) return 1;
+    /* LORADSNrm1Obj / Nrm2Obj / NrmInfObj (lorads_solver.c:222-262, lorads_alg_common.c:481-497) */
+    double n1 = 0, n2 = 0, ninf = 0;
+    if (ctx->lp.n > 0) {
+        n1 += ctx->lp.nrm1;
+        n2 += ctx->lp.nrm1 * ctx->lp.nrm1;
+        ninf = std::max(ninf, ctx->lp.nrminf_q);
+    }
+    for (const auto &c : ctx->cones) {
+        n1 += c.c_nrm1;
+        n2 += c.c_nrm2sq;
+        ninf = std::max(ninf, c.c_nrminf);
+    }
+    out[0] = n1;
+    out[1] = sqrt(n2);
+    out[2] = ninf;
+    out[3] = ctx->b_nrm1;
+    out[4] = ctx->b_nrm2;
+    out[5] = ctx->b_nrminf_q;
+    return 0;
+}
+
+extern "C" int lgpu_obj_scale(lgpu_ctx *ctx, double s)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (auto &c : ctx->cones) {
+        double *cv = c.cval, *cc = c.c_coef;
+        launch_map(ctx, c.nnzP, [=] __device__(int64_t i) { cv[i] *= s; });
+        launch_map(ctx, c.nnzC, [=] __device__(int64_t i) { cc[i] *= s; });
+        c.c_nrm1 *= fabs(s);
+        c.c_nrm2sq *= s * s;
+        c.c_nrminf *= fabs(s);
+    }
+    if (ctx->lp.n > 0) {
+        double *o = ctx->lp.obj;
+        launch_map(ctx, ctx->lp.n, [=] __device__(int64_t i) { o[i] *= s; });
+        for (auto &v : ctx->lp.h_obj) v *= s;
+    }
+    double *lam = ctx->lam;
+    launch_map(ctx, ctx->m, [=] __device__(int64_t i) { lam[i] *= s; });
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * variables
+ * ------------------------------------------------------------------------------------------------*/
+static int alloc_flat(lgpu_ctx *ctx, double **p)
+{
+    TRY(dev_alloc(ctx, p, (size_t)ctx->N));
+    CU(ctx, cudaMemsetAsync(*p, 0, sizeof(double) * ctx->N, ctx->stream));
+    return 0;
+}
+
+static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
+{
+    int64_t off = 0;
+    for (int c = 0; c < ctx->ncones; ++c) {
+        DevCone &cn = ctx->cones[c];
+        if (rank[c] <= 0 || rank[c] > cn.n) LGPU_FAIL(ctx, "bad rank %lld for cone %d", (long long)rank[c], c);
+        cn.r = rank[c];
+        cn.ld = (rank[c] + 3) & ~(int64_t)3;
+        cn.off = off;
+        off += cn.n * cn.ld;
+    }
+    ctx->lp.off = off;
+    off += ctx->lp.n;
+    ctx->N = off;
+    double **flat[] = {&ctx->R, &ctx->U, &ctx->V, &ctx->G, &ctx->M2, &ctx->bLin, &ctx->cg_r, &ctx->cg_p, &ctx->cg_Q, &ctx->stage};
+    for (auto p : flat) TRY(alloc_flat(ctx, p));
+    ctx->h = lbfgs_len;
+    ctx->head = 0;
+    ctx->s.assign(lbfgs_len, nullptr);
+    ctx->y.assign(lbfgs_len, nullptr);
+    for (int k = 0; k < lbfgs_len; ++k) {
+        TRY(alloc_flat(ctx, &ctx->s[k]));
+        TRY(alloc_flat(ctx, &ctx->y[k]));
+    }
+    ctx->vars_ready = true;
+    return 0;
+}
+
+extern "C" int lgpu_alloc_vars(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (lbfgs_len < 1 || lbfgs_len > 16) LGPU_FAIL(ctx, "lbfgs_len must be in [1,16]");
+    free_vars(ctx);
+    TRY(layout_and_alloc(ctx, rank, lbfgs_len));
+    ctx->cg_last_iter.assign(ctx->ncones, 0);
+    CU(ctx, cudaMemsetAsync(ctx->dsc, 0, sizeof(double) * LGPU_NSCALAR, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static double *flat_of(lgpu_ctx *ctx, int which)
+{
+    switch (which) {
+    case LGPU_R: return ctx->R;
+    case LGPU_U: return ctx->U;
+    case LGPU_V: return ctx->V;
+    case LGPU_GRAD: return ctx->G;
+    default: return nullptr;
+    }
+}
+static double *mvec_of(lgpu_ctx *ctx, int which)
+{
+    switch (which) {
+    case LGPU_VEC_DUAL: return ctx->lam;
+    case LGPU_VEC_CONSTR_SUM: return ctx->cvs;
+    case LGPU_VEC_ARD: return ctx->q1;
+    case LGPU_VEC_ADD: return ctx->q2;
+    case LGPU_VEC_M1: return ctx->M1;
+    case LGPU_VEC_B: return ctx->b;
+    default: return nullptr;
+    }
+}
+
+/* host column-major n x r -> device row-major n x ld at dst */
+static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *cm, double *dst)
+{
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
+    TRY(ensure_stage(ctx, bytes));
+    memcpy(ctx->hstage, cm, bytes);
+    CU(ctx, cudaMemcpyAsync(ctx->dstage, ctx->hstage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 blk(32, 8);
+    k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, dst);
+    ctx->launches++;
+    CHECK_LAUNCH(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* hstage is reused by the caller's next transfer */
+    return 0;
+}
+static int download_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *src, double *cm)
+{
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
+    TRY(ensure_stage(ctx, bytes));
+    dim3 blk(32, 8);
+    k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage);
+    ctx->launches++;
+    CHECK_LAUNCH(ctx);
+    CU(ctx, cudaMemcpyAsync(ctx->hstage, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(cm, ctx->hstage, bytes);
+    return 0;
+}
+
+extern "C" int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double *cm)
+{
+    if (!ctx || !ctx->vars_ready || cone < 0 || cone >= ctx->ncones || !flat_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off);
+}
+extern "C" int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *cm)
+{
+    if (!ctx || !ctx->vars_ready || cone < 0 || cone >= ctx->ncones || !flat_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    return download_factor(ctx, c.n, c.r, c.ld, flat_of(ctx, which) + c.off, cm);
+}
+extern "C" int lgpu_set_lp(lgpu_ctx *ctx, int which, const double *v)
+{
+    if (!ctx || !ctx->vars_ready || ctx->lp.n <= 0 || !flat_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(flat_of(ctx, which) + ctx->lp.off, v, sizeof(double) * ctx->lp.n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_get_lp(lgpu_ctx *ctx, int which, double *v)
+{
+    if (!ctx || !ctx->vars_ready || ctx->lp.n <= 0 || !flat_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(v, flat_of(ctx, which) + ctx->lp.off, sizeof(double) * ctx->lp.n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_set_vec(lgpu_ctx *ctx, int which, const double *v)
+{
+    if (!ctx || !mvec_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(mvec_of(ctx, which), v, sizeof(double) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_get_vec(lgpu_ctx *ctx, int which, double *v)
+{
+    if (!ctx || !mvec_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(v, mvec_of(ctx, which), sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_get_rank(const lgpu_ctx *ctx, int cone, int64_t *rank)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    *rank = ctx->cones[cone].r;
+    return 0;
+}
+
+extern "C" int lgpu_fill_factor_random(lgpu_ctx *ctx, int which, uint64_t seed)
+{
+    if (!ctx || !ctx->vars_ready || !flat_of(ctx, which)) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (auto &c : ctx->cones) {
+        double *p = flat_of(ctx, which) + c.off;
+        const int64_t ld = c.ld, r = c.r;
+        const uint64_t sd = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(c.off + 1);
+        launch_map(ctx, c.n * c.ld, [=] __device__(int64_t i) {
+            const int64_t col = i % ld;
+            uint64_t z = sd + (uint64_t)i * 0xBF58476D1CE4E5B9ull;
+            z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+            z ^= z >> 27; z *= 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            const double u1 = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+            z = z * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+            z ^= z >> 29; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 32;
+            const double u2 = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+            p[i] = col < r ? (u1 - u2) : 0.0; /* same distribution as rand()/RAND_MAX - rand()/RAND_MAX */
+        });
+    }
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    /* keep the old R, U, V, Grad alive while the new storage is laid out */
+    double *oR = ctx->R, *oU = ctx->U, *oV = ctx->V, *oG = ctx->G;
+    ctx->R = ctx->U = ctx->V = ctx->G = nullptr;
+    std::vector<int64_t> o_r(ctx->ncones), o_ld(ctx->ncones), o_off(ctx->ncones);
+    for (int c = 0; c < ctx->ncones; ++c) {
+        o_r[c] = ctx->cones[c].r;
+        o_ld[c] = ctx->cones[c].ld;
+        o_off[c] = ctx->cones[c].off;
+        if (new_rank[c] < o_r[c]) LGPU_FAIL(ctx, "aug_rank cannot shrink");
+    }
+    const int64_t o_lp_off = ctx->lp.off;
+    const int h = ctx->h;
+    free_vars(ctx);
+    int rc = layout_and_alloc(ctx, new_rank, h);
+    if (rc) return rc;
+    double *olds[4] = {oR, oU, oV, oG};
+    double *news[4] = {ctx->R, ctx->U, ctx->V, ctx->G};
+    for (int w = 0; w < 4; ++w) {
+        for (int c = 0; c < ctx->ncones; ++c) {
+            DevCone &cn = ctx->cones[c];
+            k_restride_aug<<<grid_for(ctx, cn.n * cn.ld), LGPU_TPB, 0, ctx->stream>>>(
+                cn.n, (int)o_r[c], (int)o_ld[c], (int)cn.r, (int)cn.ld, olds[w] + o_off[c], news[w] + cn.off, 1);
+            ctx->launches++;
+        }
+        if (ctx->lp.n > 0)
+            CU(ctx, cudaMemcpyAsync(news[w] + ctx->lp.off, olds[w] + o_lp_off, sizeof(double) * ctx->lp.n,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CHECK_LAUNCH(ctx);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(oR); cudaFree(oU); cudaFree(oV); cudaFree(oG);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A(UV^T) and friends
+ * ------------------------------------------------------------------------------------------------*/
+static void pair_ptrs(lgpu_ctx *ctx, int pair, double **A, double **B)
+{
+    switch (pair) {
+    case LGPU_PAIR_RR: *A = ctx->R; *B = ctx->R; break;
+    case LGPU_PAIR_RU: *A = ctx->R; *B = ctx->U; break;
+    case LGPU_PAIR_UU: *A = ctx->U; *B = ctx->U; break;
+    default: *A = ctx->U; *B = ctx->V; break;
+    }
+}
+
+/* per cone: uvt on the pattern, cv = A_c(.), optional objective accumulate (LORADSInitConstrValObjVal) */
+static void cones_auv(lgpu_ctx *ctx, const double *A, const double *B, int obj_slot /* -1: none */)
+{
+    for (auto &c : ctx->cones) {
+        run_uvt(ctx, c, c.ld, A + c.off, B + c.off, c.uvt);
+        if (obj_slot >= 0) run_obj_gather(ctx, c, c.uvt, obj_slot, 1);
+        run_con_gather(ctx, c, c.uvt, c.cv);
+    }
+}
+
+/* out (m-vector) = scale * ( LP part + sum over cones of expanded cv )   [InitConstrValSum / ConstrValSumALMtemp] */
+static void sum_constr_vals(lgpu_ctx *ctx, const double *A, const double *B, double scale, double *out)
+{
+    const int64_t m = ctx->m;
+    if (ctx->lp.n > 0) {
+        const int32_t *rp = ctx->lp.r_ptr, *rc = ctx->lp.r_col;
+        const double *rv = ctx->lp.r_val;
+        const double *u = A + ctx->lp.off, *v = B + ctx->lp.off;
+        launch_map(ctx, m, [=] __device__(int64_t i) {
+            double a = 0.0;
+            for (int e = rp[i]; e < rp[i + 1]; ++e) a = fma(rv[e], u[rc[e]] * v[rc[e]], a);
+            out[i] = scale * a;
+        });
+    } else {
+        cudaMemsetAsync(out, 0, sizeof(double) * m, ctx->stream);
+    }
+    for (auto &c : ctx->cones) {
+        const int32_t *gid = c.con_gid;
+        const double *cv = c.cv;
+        launch_map(ctx, c.mA, [=] __device__(int64_t t) { out[gid[t]] += scale * cv[t]; });
+    }
+}
+
+extern "C" int lgpu_init_constr_val(lgpu_ctx *ctx, int pair)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double *A, *B;
+    pair_ptrs(ctx, pair, &A, &B);
+    cones_auv(ctx, A, B, -1);
+    sum_constr_vals(ctx, A, B, 1.0, ctx->cvs);
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+/* Grad = 2 (C + A*(M1)) R for all cones (+ LP), with M1 already in ctx->M1; lag = sum |Grad|^2 */
+static void grad_from_m1(lgpu_ctx *ctx)
+{
+    for (auto &c : ctx->cones) {
+        run_wsum(ctx, c, ctx->M1, true, true, 1.0, c.S);
+        run_spmm(ctx, c, c.ld, c.S, ctx->R + c.off, 2.0, 0.0, nullptr, ctx->G + c.off);
+    }
+    if (ctx->lp.n > 0) {
+        /* ALMSetGradLP (lorads_alm.c:89-113): grad_j = 2 (c_j + a_j^T M1) r_j */
+        const int32_t *cp = ctx->lp.c_ptr, *cr = ctx->lp.c_row;
+        const double *cv = ctx->lp.c_val, *obj = ctx->lp.obj, *M1 = ctx->M1;
+        const double *r = ctx->R + ctx->lp.off;
+        double *g = ctx->G + ctx->lp.off;
+        launch_map(ctx, ctx->lp.n, [=] __device__(int64_t j) {
+            double w = obj[j];
+            for (int e = cp[j]; e < cp[j + 1]; ++e) w = fma(M1[cr[e]], cv[e], w);
+            g[j] = 2.0 * w * r[j];
+        });
+    }
+    const double *G = ctx->G;
+    launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(G[i], G[i], acc[0]); }, slot1(SC_LAG));
+}
+
+extern "C" int lgpu_alm_cal_grad(lgpu_ctx *ctx, double rho, double *lag_norm_square)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    {
+        /* M1 = -lambda - rho b + rho constrValSum (lorads_alm.c:38-50) */
+        double *M1 = ctx->M1;
+        const double *lam = ctx->lam, *b = ctx->b, *cvs = ctx->cvs;
+        launch_map(ctx, ctx->m, [=] __device__(int64_t i) { M1[i] = -lam[i] - rho * b[i] + rho * cvs[i]; });
+    }
+    grad_from_m1(ctx);
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_LAG, 1));
+    *lag_norm_square = ctx->hsc[SC_LAG];
+    return 0;
+}
+
+extern "C" int lgpu_lbfgs_direction(lgpu_ctx *ctx, int64_t inner_iter)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int64_t N = ctx->N;
+    double *D = ctx->U;
+    const double *G = ctx->G;
+    double *dsc = ctx->dsc;
+    if (inner_iter == 0) {
+        launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = -G[i]; });
+        CHECK_LAUNCH(ctx);
+        return 0; /* the reference returns before the <D,Grad> test changes anything: D = -Grad already */
+    }
+    const int h = ctx->h;
+    const int nn = (int)((inner_iter <= (ctx->lp.n > 0 ? h : h - 1)) ? inner_iter : h); /* Q4: LP variant uses <= h */
+    /* two-loop recursion (lorads_alm.c:468-505), q lives in D */
+    CU(ctx, cudaMemcpyAsync(D, G, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+    int node = (ctx->head - 1 + h) % h;
+    for (int k = 0; k < nn; ++k) {
+        const double *s = ctx->s[node], *y = ctx->y[node];
+        launch_reduce<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(s[i], D[i], acc[0]); }, slot1(SC_TMP));
+        const int ia = SC_ALPHA0 + node, ib = SC_BETA0 + node;
+        launch_scalar(ctx, [=] __device__() { dsc[ia] = dsc[ib] * dsc[SC_TMP]; });
+        launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = fma(-dsc[ia], y[i], D[i]); });
+        node = (node - 1 + h) % h;
+    }
+    node = (node + 1) % h;
+    for (int k = 0; k < nn; ++k) {
+        const double *s = ctx->s[node], *y = ctx->y[node];
+        launch_reduce<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(y[i], D[i], acc[0]); }, slot1(SC_TMP));
+        const int ia = SC_ALPHA0 + node, ib = SC_BETA0 + node;
+        launch_scalar(ctx, [=] __device__() { dsc[SC_TMP2] = dsc[ia] - dsc[ib] * dsc[SC_TMP]; });
+        launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = fma(dsc[SC_TMP2], s[i], D[i]); });
+        node = (node + 1) % h;
+    }
+    /* D = -q and <D, Grad> in one pass; then LBFGSDirectionUseGrad (lorads_alm.c:607-627) */
+    launch_reduce<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) {
+        const double d = -D[i];
+        D[i] = d;
+        acc[0] = fma(d, G[i], acc[0]);
+    }, slot1(SC_DG));
+    launch_map(ctx, N, [=] __device__(int64_t i) {
+        if (dsc[SC_DG] >= 0.0) D[i] = -G[i];
+    });
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7])
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double *dsc = ctx->dsc;
+    launch_scalar(ctx, [=] __device__() { dsc[SC_P1] = 0.0; dsc[SC_P2] = 0.0; });
+    /* ALMCalq12p12: q1 = 2 A(sym(R D^T)), p1 = 2 <C, R D^T>; q2 = A(D D^T), p2 = <C, D D^T> */
+    cones_auv(ctx, ctx->R, ctx->U, SC_P1);
+    if (ctx->lp.n > 0) {
+        const double *obj = ctx->lp.obj, *u = ctx->R + ctx->lp.off, *v = ctx->U + ctx->lp.off;
+        launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * v[j], acc[0]); }, slot1(SC_P1, 1));
+    }
+    sum_constr_vals(ctx, ctx->R, ctx->U, 2.0, ctx->q1);
+    cones_auv(ctx, ctx->U, ctx->U, SC_P2);
+    if (ctx->lp.n > 0) {
+        const double *obj = ctx->lp.obj, *u = ctx->U + ctx->lp.off;
+        launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * u[j], acc[0]); }, slot1(SC_P2, 1));
+    }
+    sum_constr_vals(ctx, ctx->U, ctx->U, 1.0, ctx->q2);
+    {
+        /* the five reductions of ALMLineSearch (lorads_alm.c:266-279); q0' = b - constrValSum + lambda / rho */
+        const double *b = ctx->b, *cvs = ctx->cvs, *lam = ctx->lam, *q1 = ctx->q1, *q2 = ctx->q2;
+        const double rinv = 1.0 / rho;
+        SlotSpec<5> sp;
+        sp.slot[0] = SC_LS0; sp.slot[1] = SC_LS1; sp.slot[2] = SC_LS2; sp.slot[3] = SC_LS3; sp.slot[4] = SC_LS4;
+        sp.accumulate = 0;
+        launch_reduce<5>(ctx, ctx->m, [=] __device__(int64_t i, double(&acc)[5]) {
+            const double q0 = (b[i] - cvs[i]) + rinv * lam[i];
+            const double a = q1[i], c2 = q2[i];
+            acc[0] = fma(c2, c2, acc[0]);
+            acc[1] = fma(a, c2, acc[1]);
+            acc[2] = fma(q0, c2, acc[2]);
+            acc[3] = fma(a, a, acc[3]);
+            acc[4] = fma(q0, a, acc[4]);
+        }, sp);
+    }
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_P1, 7));
+    out[0] = 2.0 * ctx->hsc[SC_P1];
+    out[1] = ctx->hsc[SC_P2];
+    for (int k = 0; k < 5; ++k) out[2 + k] = ctx->hsc[SC_LS0 + k];
+    return 0;
+}
+
+extern "C" int lgpu_alm_step(lgpu_ctx *ctx, double tau)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    {
+        double *yh = ctx->y[ctx->head], *R = ctx->R;
+        const double *G = ctx->G, *D = ctx->U;
+        launch_map(ctx, ctx->N, [=] __device__(int64_t i) {
+            yh[i] = -G[i];
+            R[i] = fma(tau, D[i], R[i]);
+        });
+    }
+    {
+        double *cvs = ctx->cvs;
+        const double *q1 = ctx->q1, *q2 = ctx->q2;
+        const double t2 = tau * tau;
+        launch_map(ctx, ctx->m, [=] __device__(int64_t i) { cvs[i] = fma(t2, q2[i], fma(tau, q1[i], cvs[i])); });
+    }
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int lgpu_lbfgs_push(lgpu_ctx *ctx, double tau)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double *sh = ctx->s[ctx->head], *yh = ctx->y[ctx->head];
+    const double *G = ctx->G, *D = ctx->U;
+    double *dsc = ctx->dsc;
+    launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) {
+        const double sv = tau * D[i];
+        const double yv = yh[i] + G[i];
+        sh[i] = sv;
+        yh[i] = yv;
+        acc[0] = fma(yv, sv, acc[0]);
+    }, slot1(SC_YS));
+    const int ib = SC_BETA0 + ctx->head;
+    launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
+    ctx->head = (ctx->head + 1) % ctx->h;
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int lgpu_primal_infeasibility(lgpu_ctx *ctx, int pair, double *pinf_l1)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    TRY(lgpu_init_constr_val(ctx, pair));
+    const double *b = ctx->b, *cvs = ctx->cvs;
+    launch_reduce<1>(ctx, ctx->m, [=] __device__(int64_t i, double(&acc)[1]) {
+        const double d = b[i] - cvs[i];
+        acc[0] = fma(d, d, acc[0]);
+    }, slot1(SC_PINF));
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_PINF, 1));
+    *pinf_l1 = sqrt(ctx->hsc[SC_PINF]) / (1.0 + ctx->b_nrm1);
+    return 0;
+}
+
+extern "C" int lgpu_update_dual_var(lgpu_ctx *ctx, double rho)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double *lam = ctx->lam;
+    const double *b = ctx->b, *cvs = ctx->cvs;
+    /* lambda += rho b ; lambda -= rho constrValSum (two axpys, lorads_alg_common.c:511-524) */
+    launch_map(ctx, ctx->m, [=] __device__(int64_t i) { lam[i] = fma(-rho, cvs[i], fma(rho, b[i], lam[i])); });
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int lgpu_average_uv(lgpu_ctx *ctx)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double *R = ctx->R;
+    const double *U = ctx->U, *V = ctx->V;
+    launch_map(ctx, ctx->N, [=] __device__(int64_t i) { R[i] = (U[i] + V[i]) / 2.0; });
+    CHECK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int lgpu_cal_obj(lgpu_ctx *ctx, int admm, double *pobj)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (admm) TRY(lgpu_average_uv(ctx));
+    double *dsc = ctx->dsc;
+    launch_scalar(ctx, [=] __device__() { dsc[SC_OBJ] = 0.0; });
+    if (ctx->lp.n > 0) {
+        const double *obj = ctx->lp.obj, *u = ctx->R + ctx->lp.off;
+        launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * u[j], acc[0]); }, slot1(SC_OBJ, 1));
+    }
+    for (auto &c : ctx->cones) {
+        run_uvt(ctx, c, c.ld, ctx->R + c.off, ctx->R + c.off, c.uvt);
+        run_obj_gather(ctx, c, c.uvt, SC_OBJ, 1);
+    }
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_OBJ, 1));
+    *pobj = ctx->hsc[SC_OBJ];
+    return 0;
+}
+
+extern "C" int lgpu_cal_dual_obj(lgpu_ctx *ctx, double *dobj)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const double *b = ctx->b, *lam = ctx->lam;
+    launch_reduce<1>(ctx, ctx->m, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(b[i], lam[i], acc[0]); }, slot1(SC_DOBJ));
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_DOBJ, 1));
+    *dobj = ctx->hsc[SC_DOBJ];
+    return 0;
+}
+
+extern "C" int lgpu_alm_to_admm(lgpu_ctx *ctx)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(ctx->V, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->U, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_copy_r_to_v(lgpu_ctx *ctx)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(ctx->V, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ADMM: CG on x -> x + (sum_i <A_i, sym(x V^T)> A_i) V          lorads_admm.c:442-616, lorads_cgs.c:128-287
+ * ------------------------------------------------------------------------------------------------*/
+/* res = x + A_V^*(A_V(x)) V for cone c; x, fixed, res are row-major blocks of that cone */
+static void cg_mvec(lgpu_ctx *ctx, DevCone &c, const double *x, const double *fixed, double *res)
+{
+    /* LORADSUpdateConstrValCG: weight = A(sym(x V^T)) ; then w_sum = sum weight_i A_i ; res = w_sum V + x */
+    run_uvt(ctx, c, c.ld, x, fixed, c.uvt);
+    run_con_gather(ctx, c, c.uvt, c.wtmp);
+    run_wsum(ctx, c, c.wtmp, false, false, 1.0, c.S);
+    run_spmm(ctx, c, c.ld, c.S, fixed, 1.0, 1.0, x, res);
+}
+
+static int cg_solve(lgpu_ctx *ctx, int ci, double *x, const double *fixed, const double *bvec, double tol, int64_t maxit,
+                    int64_t *iters)
+{
+    DevCone &c = ctx->cones[ci];
+    const int64_t nr = c.n * c.ld;
+    double *r = ctx->cg_r + c.off, *p = ctx->cg_p + c.off, *Q = ctx->cg_Q + c.off;
+    double *dsc = ctx->dsc;
+    /* bNorm = |b|_1 ; r = b - M x ; resiNorm */
+    launch_reduce<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] += fabs(bvec[i]); }, slot1(SC_CG_B1));
+    cg_mvec(ctx, c, x, fixed, r);
+    launch_reduce<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) {
+        const double v = bvec[i] - r[i];
+        r[i] = v;
+        acc[0] = fma(v, v, acc[0]);
+    }, slot1(SC_CG_RES));
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_CG_RR, SC_CG_BETA - SC_CG_RR + 1));
+    const double bnorm = ctx->hsc[SC_CG_B1];
+    double res = sqrt(ctx->hsc[SC_CG_RES]);
+    if (res / bnorm < tol) {
+        *iters = ctx->cg_last_iter[ci]; /* quirk: cg->iter is not reset on this early exit (lorads_cgs.c:204-217) */
+        return 0;
+    }
+    CU(ctx, cudaMemcpyAsync(p, r, sizeof(double) * nr, cudaMemcpyDeviceToDevice, ctx->stream));
+    int64_t it = 0;
+    for (int64_t k = 0; k < maxit; ++k) {
+        it += 1;
+        cg_mvec(ctx, c, p, fixed, Q);
+        {
+            SlotSpec<2> sp;
+            sp.slot[0] = SC_CG_RR; sp.slot[1] = SC_CG_PQ; sp.accumulate = 0;
+            launch_reduce<2>(ctx, nr, [=] __device__(int64_t i, double(&acc)[2]) {
+                acc[0] = fma(r[i], r[i], acc[0]);
+                acc[1] = fma(p[i], Q[i], acc[1]);
+            }, sp);
+        }
+        launch_scalar(ctx, [=] __device__() { dsc[SC_CG_ALPHA] = dsc[SC_CG_RR] / dsc[SC_CG_PQ]; });
+        launch_reduce<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) {
+            const double a = dsc[SC_CG_ALPHA];
+            x[i] = fma(a, p[i], x[i]);
+            const double v = fma(-a, Q[i], r[i]);
+            r[i] = v;
+            acc[0] = fma(v, v, acc[0]);
+        }, slot1(SC_CG_RES));
+        CHECK_LAUNCH(ctx);
+        TRY(fetch_scalars(ctx, SC_CG_RES, 1));
+        res = sqrt(ctx->hsc[SC_CG_RES]);
+        if (res / bnorm < tol) break;
+        if (k % 20 == 0) {
+            /* residual recomputed from scratch, p = q = r (lorads_cgs.c:242-258); the update below then runs with
+             * beta = 1, i.e. p = 2 r -- reproduced as is */
+            cg_mvec(ctx, c, x, fixed, r);
+            launch_reduce<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double v = bvec[i] - r[i];
+                r[i] = v;
+                p[i] = v;
+                acc[0] = fma(v, v, acc[0]);
+            }, slot1(SC_CG_RR));
+            /* qTrNew = r.r = qTr -> beta = qTrNew / qTr (1 unless r.r is 0/NaN) */
+            launch_scalar(ctx, [=] __device__() { dsc[SC_CG_BETA] = dsc[SC_CG_RR] / dsc[SC_CG_RR]; });
+        } else {
+            /* beta = (r_new . r_new) / (r_old . r_old): numerator is SC_CG_RES, denominator SC_CG_RR */
+            launch_scalar(ctx, [=] __device__() { dsc[SC_CG_BETA] = dsc[SC_CG_RES] / dsc[SC_CG_RR]; });
+        }
+        launch_map(ctx, nr, [=] __device__(int64_t i) { p[i] = fma(dsc[SC_CG_BETA], p[i], r[i]); });
+    }
+    ctx->cg_last_iter[ci] = it;
+    *iters = it;
+    return 0;
+}
+
+/* LORADSUpdateSDPVarOne for cone ci: update `upd` with `fixed` held (lorads_admm.c:564-616) */
+static int admm_update_one(lgpu_ctx *ctx, int ci, double *upd_flat, const double *fixed_flat, double rho, double tol,
+                           int64_t maxit, int64_t *iters)
+{
+    DevCone &c = ctx->cones[ci];
+    const int64_t m = ctx->m;
+    {
+        /* M1 = rho (-b + constrValSum - constrVal_c) - lambda */
+        double *M1 = ctx->M1;
+        const double *b = ctx->b, *cvs = ctx->cvs, *lam = ctx->lam;
+        launch_map(ctx, m, [=] __device__(int64_t i) { M1[i] = -b[i] + cvs[i]; });
+        const int32_t *gid = c.con_gid;
+        const double *cv = c.cv;
+        launch_map(ctx, c.mA, [=] __device__(int64_t t) { M1[gid[t]] -= cv[t]; });
+        launch_map(ctx, m, [=] __device__(int64_t i) { M1[i] = rho * M1[i] - lam[i]; });
+    }
+    double *upd = upd_flat + c.off;
+    const double *fixed = fixed_flat + c.off;
+    double *M2 = ctx->M2 + c.off, *bl = ctx->bLin + c.off;
+    run_wsum(ctx, c, ctx->M1, true, true, 1.0, c.S);
+    /* M2 = S V - rho V ; bLinSys = -M2 / rho */
+    run_spmm(ctx, c, c.ld, c.S, fixed, 1.0, -rho, fixed, M2);
+    {
+        const double sc = -1.0 / rho;
+        launch_map(ctx, c.n * c.ld, [=] __device__(int64_t i) { bl[i] = sc * M2[i]; });
+    }
+    TRY(cg_solve(ctx, ci, upd, fixed, bl, tol, maxit, iters));
+    return 0;
+}
+
+/* after a U- or V-update of cone c: constrValSum -= old cv ; cv = A(UV^T) ; constrValSum += cv */
+static void refresh_cone_cv(lgpu_ctx *ctx, DevCone &c)
+{
+    const int32_t *gid = c.con_gid;
+    double *cv = c.cv, *cvs = ctx->cvs;
+    launch_map(ctx, c.mA, [=] __device__(int64_t t) { cvs[gid[t]] -= cv[t]; });
+    run_uvt(ctx, c, c.ld, ctx->U + c.off, ctx->V + c.off, c.uvt);
+    run_con_gather(ctx, c, c.uvt, c.cv);
+    launch_map(ctx, c.mA, [=] __device__(int64_t t) { cvs[gid[t]] += cv[t]; });
+}
+
+/* LORADSUpdateLPVarOne sweep on the host (lorads_admm.c:759-792, lorads_alg_common.c:356-374): the LP block is a
+ * strictly sequential Gauss-Seidel over scalar columns; it works on host copies of the m-vectors. */
+static int admm_lp_sweep(lgpu_ctx *ctx, double rho)
+{
+    DevLp &lp = ctx->lp;
+    const int64_t m = ctx->m, n = lp.n;
+    std::vector<double> cvs(m), lam(m), u(n), v(n);
+    CU(ctx, cudaMemcpyAsync(cvs.data(), ctx->cvs, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(lam.data(), ctx->lam, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(u.data(), ctx->U + lp.off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(v.data(), ctx->V + lp.off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const std::vector<double> &b = ctx->h_b;
+    for (int64_t j = 0; j < n; ++j) {
+        const int32_t e0 = lp.h_c_ptr[j], e1 = lp.h_c_ptr[j + 1];
+        for (int pass = 0; pass < 2; ++pass) {
+            double *upd = pass == 0 ? &u[j] : &v[j];
+            const double fixed = pass == 0 ? v[j] : u[j];
+            const double uv_old = u[j] * v[j];
+            double w = lp.h_obj[j];
+            for (int32_t e = e0; e < e1; ++e) {
+                const int32_t i = lp.h_c_row[e];
+                const double m1 = rho * (-b[i] + cvs[i] - lp.h_c_val[e] * uv_old) - lam[i];
+                w += m1 * lp.h_c_val[e];
+            }
+            double M2 = w * fixed;
+            M2 = M2 - rho * fixed;
+            const double blin = -1.0 * M2 / rho;
+            *upd = blin / (1 + lp.h_nrm2sq[j] * fixed * fixed);
+            const double uv_new = u[j] * v[j];
+            for (int32_t e = e0; e < e1; ++e) {
+                const int32_t i = lp.h_c_row[e];
+                cvs[i] -= lp.h_c_val[e] * uv_old;
+                cvs[i] += lp.h_c_val[e] * uv_new;
+            }
+        }
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->cvs, cvs.data(), sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->U + lp.off, u.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->V + lp.off, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lgpu_admm_update_var(lgpu_ctx *ctx, double rho, double cg_tol, int64_t cg_max_iter, int64_t *cg_iter_total)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int ci = 0; ci < ctx->ncones; ++ci) {
+        DevCone &c = ctx->cones[ci];
+        int64_t it = 0;
+        TRY(admm_update_one(ctx, ci, ctx->U, ctx->V, rho, cg_tol, cg_max_iter, &it));
+        *cg_iter_total += it;
+        refresh_cone_cv(ctx, c);
+        TRY(admm_update_one(ctx, ci, ctx->V, ctx->U, rho, cg_tol, cg_max_iter, &it));
+        *cg_iter_total += it;
+        refresh_cone_cv(ctx, c);
+    }
+    CHECK_LAUNCH(ctx);
+    if (ctx->lp.n > 0) TRY(admm_lp_sweep(ctx, rho));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * oracle-rank Gram
+ * ------------------------------------------------------------------------------------------------*/
+extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
+{
+    if (!ctx || !ctx->vars_ready || cone < 0 || cone >= ctx->ncones) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    const int r = (int)c.r;
+    const int nt = (r + 15) / 16;
+    int64_t rows_per_chunk = 4096;
+    int nchunks = (int)((c.n + rows_per_chunk - 1) / rows_per_chunk);
+    const size_t part_bytes = sizeof(double) * (size_t)nchunks * nt * nt * 256;
+    const size_t gram_bytes = sizeof(double) * (size_t)r * r;
+    TRY(ensure_dstage(ctx, part_bytes + gram_bytes));
+    double *part = (double *)ctx->dstage;
+    double *dg = part + (size_t)nchunks * nt * nt * 256;
+    const double *A = (phase == 1 ? ctx->R : ctx->U) + c.off;
+    const double *B = ctx->V + c.off;
+    dim3 grid(nchunks, nt * nt);
+    k_gram_partial<<<grid, 256, 0, ctx->stream>>>(c.n, r, (int)c.ld, A, B, phase == 1 ? 0 : 1, rows_per_chunk, part);
+    k_gram_finish<<<nt * nt, 256, 0, ctx->stream>>>(nchunks, nt * nt, r, part, dg);
+    ctx->launches += 2;
+    CHECK_LAUNCH(ctx);
+    CU(ctx, cudaMemcpyAsync(gram, dg, gram_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * dual infeasibility: lambda_min(C - A*(lambda)) per cone by Lanczos on the device
+ * ------------------------------------------------------------------------------------------------*/
+static double tridiag_min_eig(const std::vector<double> &a, const std::vector<double> &b, int k)
+{
+    double lo = a[0], hi = a[0];
+    for (int i = 0; i < k; ++i) {
+        double rr = 0.0;
+        if (i > 0) rr += fabs(b[i - 1]);
+        if (i < k - 1) rr += fabs(b[i]);
+        lo = std::min(lo, a[i] - rr);
+        hi = std::max(hi, a[i] + rr);
+    }
+    for (int it = 0; it < 200; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        int cnt = 0;
+        double d = a[0] - mid;
+        if (d < 0) cnt++;
+        for (int i = 1; i < k; ++i) {
+            const double dd = (d == 0.0) ? 1e-300 : d;
+            d = a[i] - mid - b[i - 1] * b[i - 1] / dd;
+            if (d < 0) cnt++;
+        }
+        if (cnt >= 1) hi = mid; else lo = mid;
+        if (hi - lo <= 1e-15 * (fabs(lo) + fabs(hi)) + 1e-300) break;
+    }
+    return 0.5 * (lo + hi);
+}
+
+extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double total = 0.0;
+    /* LP part (lorads_solver.c:1404-1412): |min(c_j - a_j^T lambda, 0)| */
+    if (ctx->lp.n > 0) {
+        std::vector<double> lam(ctx->m);
+        CU(ctx, cudaMemcpyAsync(lam.data(), ctx->lam, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t j = 0; j < ctx->lp.n; ++j) {
+            double w = ctx->lp.h_obj[j];
+            for (int32_t e = ctx->lp.h_c_ptr[j]; e < ctx->lp.h_c_ptr[j + 1]; ++e) w += -lam[ctx->lp.h_c_row[e]] * ctx->lp.h_c_val[e];
+            total += fabs(std::min(w, 0.0));
+        }
+    }
+    double *dsc = ctx->dsc;
+    for (auto &c : ctx->cones) {
+        const int64_t n = c.n;
+        int kmax = (int)std::min<int64_t>(n, 300);
+        {
+            const int64_t by_mem = (int64_t)(6.0e9 / (8.0 * (double)n)) - 2; /* keep the Krylov basis under ~6 GB */
+            if (by_mem < kmax) kmax = (int)std::max<int64_t>(by_mem, 20);
+        }
+        /* slack S = C - sum lambda_i A_i on the pattern */
+        run_wsum(ctx, c, ctx->lam, true, true, -1.0, c.S);
+        const size_t vec = (size_t)n;
+        TRY(ensure_dstage(ctx, sizeof(double) * vec * ((size_t)kmax + 2)));
+        double *Q = (double *)ctx->dstage;
+        double *w = Q + vec * ((size_t)kmax + 1);
+        {
+            double *q0 = Q;
+            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
+                uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+                z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+                const double v = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+                q0[i] = v;
+                acc[0] = fma(v, v, acc[0]);
+            }, slot1(SC_LANCZOS));
+            launch_map(ctx, n, [=] __device__(int64_t i) { q0[i] /= sqrt(dsc[SC_LANCZOS]); });
+        }
+        std::vector<double> al, be;
+        double theta = 0.0, theta_prev = 1e300;
+        const int32_t *fp = c.f_ptr, *fc = c.f_col, *fs = c.f_slot;
+        const double *Sv = c.S;
+        for (int k = 0; k < kmax; ++k) {
+            double *qk = Q + vec * (size_t)k;
+            /* w = S q_k  (sdp_coeff.mv, lorads_sdp_data.c:772-787,983-1006) and alpha_k = <q_k, w> */
+            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
+                double a = 0.0;
+                for (int e = fp[i]; e < fp[i + 1]; ++e) a = fma(Sv[fs[e]], qk[fc[e]], a);
+                w[i] = a;
+                acc[0] = fma(qk[i], a, acc[0]);
+            }, slot1(SC_LANCZOS));
+            CHECK_LAUNCH(ctx);
+            TRY(fetch_scalars(ctx, SC_LANCZOS, 1));
+            al.push_back(ctx->hsc[SC_LANCZOS]);
+            /* full re-orthogonalisation, twice */
+            for (int pass = 0; pass < 2; ++pass)
+                for (int j = 0; j <= k; ++j) {
+                    const double *qj = Q + vec * (size_t)j;
+                    launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(qj[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 1));
+                    launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS + 1], qj[i], w[i]); });
+                }
+            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 2));
+            CHECK_LAUNCH(ctx);
+            TRY(fetch_scalars(ctx, SC_LANCZOS + 2, 1));
+            const double bnorm = sqrt(ctx->hsc[SC_LANCZOS + 2]);
+            be.push_back(bnorm);
+            theta_prev = theta;
+            theta = tridiag_min_eig(al, be, k + 1);
+            bool conv = false;
+            if (k >= 1 && fabs(theta - theta_prev) <= 1e-6 * (fabs(theta) + 1e-12)) conv = true;
+            if (bnorm <= 1e-14 * (fabs(al.back()) + 1.0)) conv = true;
+            if (conv || k + 1 >= kmax) break;
+            double *qn = Q + vec * (size_t)(k + 1);
+            const double inv = 1.0 / bnorm;
+            launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * inv; });
+        }
+        total += fabs(std::min(theta, 0.0));
+    }
+    *sum_neg_eig = total;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * operator-level entry points on host buffers
+ * ------------------------------------------------------------------------------------------------*/
+struct TmpLayout {
+    int64_t ld = 0;
+    double *U = nullptr, *V = nullptr, *Y = nullptr;
+};
+
+/* temporary row-major copies of host factors with rank r for cone c (independent of the solver variables) */
+static int op_stage_factors(lgpu_ctx *ctx, DevCone &c, int64_t r, const double *U, const double *V, bool needY, TmpLayout *t)
+{
+    if (r <= 0) LGPU_FAIL(ctx, "bad rank");
+    t->ld = (r + 3) & ~(int64_t)3;
+    const size_t sz = (size_t)c.n * t->ld;
+    CU(ctx, cudaMalloc((void **)&t->U, sizeof(double) * sz));
+    TRY(upload_factor(ctx, c.n, r, t->ld, U, t->U));
+    if (V != nullptr && V != U) {
+        CU(ctx, cudaMalloc((void **)&t->V, sizeof(double) * sz));
+        TRY(upload_factor(ctx, c.n, r, t->ld, V, t->V));
+    } else {
+        t->V = t->U;
+    }
+    if (needY) CU(ctx, cudaMalloc((void **)&t->Y, sizeof(double) * sz));
+    return 0;
+}
+static void op_free(TmpLayout *t)
+{
+    if (t->V && t->V != t->U) cudaFree(t->V);
+    if (t->U) cudaFree(t->U);
+    if (t->Y) cudaFree(t->Y);
+}
+
+extern "C" int lgpu_op_uvt(lgpu_ctx *ctx, int cone, int64_t r, const double *U, const double *V, double *uvt)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    TmpLayout t;
+    int rc = op_stage_factors(ctx, c, r, U, V, false, &t);
+    if (!rc) {
+        run_uvt(ctx, c, t.ld, t.U, t.V, c.uvt);
+        cudaError_t e = cudaMemcpyAsync(uvt, c.uvt, sizeof(double) * c.nnzP, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; }
+    }
+    op_free(&t);
+    return rc;
+}
+
+extern "C" int lgpu_op_auv(lgpu_ctx *ctx, int cone, int64_t r, const double *U, const double *V, double *constr_val, double *obj)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    TmpLayout t;
+    int rc = op_stage_factors(ctx, c, r, U, V, false, &t);
+    if (!rc) {
+        double *dsc = ctx->dsc;
+        launch_scalar(ctx, [=] __device__() { dsc[SC_OBJ] = 0.0; });
+        run_uvt(ctx, c, t.ld, t.U, t.V, c.uvt);
+        run_obj_gather(ctx, c, c.uvt, SC_OBJ, 1);
+        run_con_gather(ctx, c, c.uvt, c.cv);
+        double *out = ctx->mtmp;
+        cudaMemsetAsync(out, 0, sizeof(double) * ctx->m, ctx->stream);
+        const int32_t *gid = c.con_gid;
+        const double *cv = c.cv;
+        launch_map(ctx, c.mA, [=] __device__(int64_t q) { out[gid[q]] = cv[q]; });
+        cudaError_t e = cudaMemcpyAsync(constr_val, out, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; }
+        if (!rc) rc = fetch_scalars(ctx, SC_OBJ, 1);
+        if (!rc && obj) *obj = ctx->hsc[SC_OBJ];
+    }
+    op_free(&t);
+    return rc;
+}
+
+static int op_upload_w(lgpu_ctx *ctx, const double *w)
+{
+    CU(ctx, cudaMemcpyAsync(ctx->mtmp, w, sizeof(double) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int lgpu_op_wsum(lgpu_ctx *ctx, int cone, const double *w, int add_obj, double *S)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    TRY(op_upload_w(ctx, w));
+    run_wsum(ctx, c, ctx->mtmp, true, add_obj != 0, 1.0, c.S);
+    CHECK_LAUNCH(ctx);
+    CU(ctx, cudaMemcpyAsync(S, c.S, sizeof(double) * c.nnzP, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lgpu_op_wsum_mulrk(lgpu_ctx *ctx, int cone, int64_t r, const double *w, int add_obj, const double *X, double *Y)
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevCone &c = ctx->cones[cone];
+    TmpLayout t;
+    int rc = op_stage_factors(ctx, c, r, X, nullptr, true, &t);
+    if (!rc) rc = op_upload_w(ctx, w);
+    if (!rc) {
+        run_wsum(ctx, c, ctx->mtmp, true, add_obj != 0, 1.0, c.S);
+        run_spmm(ctx, c, t.ld, c.S, t.U, 1.0, 0.0, nullptr, t.Y);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; }
+        if (!rc) rc = download_factor(ctx, c.n, r, t.ld, t.Y, Y);
+    }
+    op_free(&t);
+    return rc;
+}

@@ -1,0 +1,144 @@
+/*
+ * lgpu_internal.h -- internal structures of liblorads_b200.so (not part of the C ABI).
+ *
+ * Data layout in HBM (DESIGN.md "Data layout"):
+ *   factors   row-major n x ld doubles, ld = r rounded up to a multiple of 4 (32-byte rows), padding
+ *             columns are identically zero in every vector so flat BLAS-1 style kernels can run over
+ *             the padded storage.  All cones (and the LP scalars behind them) live in ONE flat buffer
+ *             per variable so L-BFGS / vector kernels are single launches over N = sum n_c ld_c + nLp.
+ *   cone data uploaded once: aggregated lower pattern (row,col), C on the pattern, constraints as
+ *             CSR-by-constraint over pattern slots, the slot-transposed CSR (so A*(w) is a gather, no
+ *             atomics), and the full symmetric CSR (row -> (col, slot)) for the SpMM.
+ */
+#ifndef LGPU_INTERNAL_H
+#define LGPU_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#define LGPU_NSCALAR 256
+#define LGPU_MAX_PARTIAL_BLOCKS 1184 /* 148 SMs x 8 resident CTAs of 256 threads */
+
+/* device scalar slots (ctx->dsc) */
+enum {
+    SC_TMP = 0,
+    SC_TMP2,
+    SC_NEG,
+    SC_LAG,    /* sum |Grad|^2 */
+    SC_DG,     /* <D, Grad> */
+    SC_P1,     /* <C, R D^T> accumulated over cones (not yet doubled) */
+    SC_P2,     /* <C, D D^T> */
+    SC_LS0,    /* |q2|^2 */
+    SC_LS1,    /* q1.q2 */
+    SC_LS2,    /* q0'.q2 */
+    SC_LS3,    /* |q1|^2 */
+    SC_LS4,    /* q0'.q1 */
+    SC_PINF,   /* |b - A|^2 */
+    SC_OBJ,    /* <C, RR^T> */
+    SC_DOBJ,   /* b^T lambda */
+    SC_YS,     /* <y, s> */
+    SC_CG_RR,  /* r.r */
+    SC_CG_PQ,  /* p.Q */
+    SC_CG_ALPHA,
+    SC_CG_NEGALPHA,
+    SC_CG_RES, /* |r|^2 after update */
+    SC_CG_B1,  /* |b|_1 */
+    SC_CG_BETA,
+    SC_ALPHA0, /* L-BFGS alpha[node], LGPU_MAX_HIST slots */
+    SC_BETA0 = SC_ALPHA0 + 16, /* L-BFGS beta[node] */
+    SC_LANCZOS = SC_BETA0 + 16,
+    SC_END = SC_LANCZOS + 8
+};
+
+struct DevCone {
+    /* sizes */
+    int64_t n = 0;       /* block dimension */
+    int64_t mA = 0;      /* number of non-zero constraints in this block */
+    int64_t nnzP = 0;    /* aggregated lower pattern */
+    int64_t nnzA = 0;    /* sum_i nnz(A_i) */
+    int64_t nnzC = 0;
+    int64_t nnzF = 0;    /* full symmetric pattern = 2 nnzP - #diag */
+    /* reference storage classes (for parity of the rules; the device layout is uniform) */
+    int obj_type = 0;
+    bool dense_aggregate = false;
+    bool sparse_container = false;
+    bool diag_only = false; /* every non-zero A_i is one diagonal entry (MaxCut-type) */
+    int64_t max_con_len = 0;
+    int64_t max_slot_len = 0;
+    /* C norms */
+    double c_nrm1 = 0, c_nrm2sq = 0, c_nrminf = 0;
+    /* host copies kept for lgpu_cone_pattern */
+    std::vector<int32_t> h_pat_row, h_pat_col;
+    /* device arrays */
+    int32_t *pat_row = nullptr, *pat_col = nullptr;
+    double *cval = nullptr;                      /* [nnzP] C on the pattern */
+    int32_t *c_slot = nullptr; double *c_coef = nullptr; /* [nnzC] (2-delta) c */
+    int32_t *a_ptr = nullptr, *a_slot = nullptr; double *a_coef = nullptr; /* CSR by constraint, coef=(2-delta)a */
+    int32_t *con_gid = nullptr;                  /* [mA] global constraint index */
+    int32_t *t_ptr = nullptr, *t_loc = nullptr, *t_gid = nullptr; double *t_val = nullptr; /* by slot */
+    int32_t *f_ptr = nullptr, *f_col = nullptr, *f_slot = nullptr; /* full CSR */
+    int32_t *d_row = nullptr; double *d_val = nullptr; /* diag_only: row and value per constraint */
+    /* scratch */
+    double *uvt = nullptr;  /* [nnzP] */
+    double *S = nullptr;    /* [nnzP] aggregate values (sdp_obj_sum / sdp_coeff_w_sum / slack) */
+    double *cv = nullptr;   /* [mA] constrVal of this cone (compact) */
+    double *wtmp = nullptr; /* [mA] CG weight vector (compact) */
+    /* variables */
+    int64_t r = 0, ld = 0;
+    int64_t off = 0;        /* offset of this cone inside the flat factor buffers */
+};
+
+struct DevLp {
+    int64_t n = 0;          /* number of LP columns */
+    int64_t nnz = 0;
+    double *obj = nullptr;  /* [n] */
+    /* by constraint (AUV): y_i += sum a_ij u_j v_j */
+    int32_t *r_ptr = nullptr, *r_col = nullptr; double *r_val = nullptr;
+    /* by column (WSum) */
+    int32_t *c_ptr = nullptr, *c_row = nullptr; double *c_val = nullptr;
+    double *nrm2sq = nullptr; /* [n] |a_j|^2 (host copy below) */
+    std::vector<double> h_obj, h_nrm2sq;
+    std::vector<int32_t> h_c_ptr, h_c_row; std::vector<double> h_c_val;
+    double nrm1 = 0, nrminf_q = 0;
+    int64_t off = 0;        /* offset inside the flat buffers */
+};
+
+struct lgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int num_sms = 148;
+
+    int64_t m = 0;
+    int ncones = 0;
+    std::vector<DevCone> cones;
+    DevLp lp;
+    std::vector<double> h_b;
+    double b_nrm1 = 0, b_nrm2 = 0, b_nrminf_q = 0;
+
+    /* m-vectors */
+    double *b = nullptr, *lam = nullptr, *cvs = nullptr, *q1 = nullptr, *q2 = nullptr, *M1 = nullptr,
+           *mtmp = nullptr;
+    /* flat N-vectors */
+    int64_t N = 0;
+    bool vars_ready = false;
+    double *R = nullptr, *U = nullptr, *V = nullptr, *G = nullptr, *M2 = nullptr, *bLin = nullptr,
+           *cg_r = nullptr, *cg_p = nullptr, *cg_Q = nullptr, *stage = nullptr;
+    int h = 0, head = 0;
+    std::vector<double *> s, y;
+    std::vector<int64_t> cg_last_iter; /* per cone: cg->iter persists across calls (reference quirk) */
+
+    /* scalars and reduction scratch */
+    double *dsc = nullptr;      /* device scalars */
+    double *hsc = nullptr;      /* pinned host mirror */
+    double *partials = nullptr; /* [8 * LGPU_MAX_PARTIAL_BLOCKS] */
+    unsigned int *counter = nullptr;
+    /* generic staging for host<->device operator calls */
+    double *hstage = nullptr; size_t hstage_bytes = 0;
+    void *dstage = nullptr; size_t dstage_bytes = 0;
+};
+
+#endif

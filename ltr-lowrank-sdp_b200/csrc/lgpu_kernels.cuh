@@ -1,0 +1,439 @@
+/*
+ * lgpu_kernels.cuh -- hand-written sm_100a kernels of the LoRADS inner loop.
+ *
+ * Every kernel here is HBM-bandwidth bound FP64 work (<= 0.25 flop/byte): gathers over row-major
+ * factor rows, CSR walks, flat vector algebra and deterministic reductions.  The rules that matter
+ * are coalescing (a sub-warp group of G lanes owns one factor row and reads it as consecutive
+ * 16-byte double2 words), enough loads in flight (grid-stride loops, grids sized in multiples of the
+ * 148 SMs) and no atomics on the data path (reductions are two-stage with a fixed summation order,
+ * so results are bit-reproducible run to run).
+ *
+ * Reference functions restated by each kernel are cited at the kernel.
+ */
+#ifndef LGPU_KERNELS_CUH
+#define LGPU_KERNELS_CUH
+
+#include "lgpu_internal.h"
+
+#define LGPU_TPB 256
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int K>
+struct SlotSpec {
+    int slot[K];
+    int accumulate; /* 1: dsc[slot] += result, 0: dsc[slot] = result */
+};
+
+/* Deterministic grid reduction tail: block-sum K values, publish per-block partials, the LAST block
+ * to arrive sums the partials in a fixed (thread-strided, then tree) order and writes dsc[slot]. */
+template <int K>
+__device__ __forceinline__ void grid_reduce_finish(double (&v)[K], double *partials, unsigned int *counter,
+                                                   double *dsc, const SlotSpec<K> &spec)
+{
+    __shared__ double sh[K][LGPU_TPB / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double w = warp_sum(v[k]);
+        if (lane == 0) sh[k][wid] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double t = 0.0;
+            for (int w = 0; w < LGPU_TPB / 32; ++w) t += sh[k][w];
+            partials[(size_t)k * gridDim.x + blockIdx.x] = t;
+        }
+        __threadfence();
+        unsigned int done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += LGPU_TPB)
+            t += ((volatile double *)partials)[(size_t)k * gridDim.x + i];
+        t = warp_sum(t);
+        __syncthreads();
+        if (lane == 0) sh[k][wid] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double t = 0.0;
+            for (int w = 0; w < LGPU_TPB / 32; ++w) t += sh[k][w];
+            if (spec.accumulate) dsc[spec.slot[k]] += t;
+            else dsc[spec.slot[k]] = t;
+        }
+        *counter = 0u;
+    }
+}
+
+/* generic flat kernels: f is a __device__ lambda */
+template <class F>
+__global__ void __launch_bounds__(LGPU_TPB) k_map(int64_t n, F f)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+template <int K, class F>
+__global__ void __launch_bounds__(LGPU_TPB) k_reduce(int64_t n, F f, double *partials, unsigned int *counter,
+                                                     double *dsc, SlotSpec<K> spec)
+{
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
+    grid_reduce_finish<K>(acc, partials, counter, dsc, spec);
+}
+
+template <class F>
+__global__ void k_scalar(F f)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) f();
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  pattern samples of (U V^T + V U^T)/2          reference: LORADSUVt, lorads_alg_common.c:43-90
+ * One group of G lanes per pattern entry (row i >= col j); each lane reads double2 words of the two
+ * (or four) factor rows, group-shuffle reduction, one 8-byte store per entry.
+ * ------------------------------------------------------------------------------------------------*/
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_uvt(int64_t nnzP, const int32_t *__restrict__ prow,
+                                                  const int32_t *__restrict__ pcol, const double *__restrict__ U,
+                                                  const double *__restrict__ V, int ld, int same,
+                                                  double *__restrict__ out)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    /* all lanes of a warp run the same number of iterations so the shuffles stay convergent */
+    const int64_t iters = (nnzP + groups - 1) / groups;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t k = g0 + it * groups;
+        const bool live = k < nnzP;
+        double a1 = 0.0, a2 = 0.0;
+        int i = 0, j = 0;
+        if (live) {
+            i = prow[k];
+            j = pcol[k];
+            const double2 *Ui = reinterpret_cast<const double2 *>(U + (size_t)i * ld);
+            const double2 *Vj = reinterpret_cast<const double2 *>(V + (size_t)j * ld);
+            if (i == j || same) {
+                for (int c = lane; c < ld2; c += G) {
+                    double2 u = Ui[c], v = Vj[c];
+                    a1 = fma(u.x, v.x, a1);
+                    a1 = fma(u.y, v.y, a1);
+                }
+                a2 = a1;
+            } else {
+                const double2 *Uj = reinterpret_cast<const double2 *>(U + (size_t)j * ld);
+                const double2 *Vi = reinterpret_cast<const double2 *>(V + (size_t)i * ld);
+                for (int c = lane; c < ld2; c += G) {
+                    double2 u = Ui[c], v = Vj[c], uu = Uj[c], vv = Vi[c];
+                    a1 = fma(u.x, v.x, a1);
+                    a1 = fma(u.y, v.y, a1);
+                    a2 = fma(uu.x, vv.x, a2);
+                    a2 = fma(uu.y, vv.y, a2);
+                }
+            }
+        }
+        a1 = group_sum<G>(a1);
+        a2 = group_sum<G>(a2);
+        if (live && lane == 0) out[k] = (i == j) ? a1 : (0.5 * a1 + 0.5 * a2);
+    }
+}
+
+/* diag_only cones, CG operator: only the diagonal samples are ever read (A_i = a e_d e_d^T)
+ * cv[t] = a_t * <U_d, V_d>                 reference: sdp*ConeAUVImpl on 1-entry diagonal constraints */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_diag_auv(int64_t mA, const int32_t *__restrict__ drow,
+                                                       const double *__restrict__ dval, const double *__restrict__ U,
+                                                       const double *__restrict__ V, int ld, double *__restrict__ cv)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (mA + groups - 1) / groups;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t t = g0 + it * groups;
+        const bool live = t < mA;
+        double a = 0.0;
+        if (live) {
+            const int i = drow[t];
+            const double2 *Ui = reinterpret_cast<const double2 *>(U + (size_t)i * ld);
+            const double2 *Vi = reinterpret_cast<const double2 *>(V + (size_t)i * ld);
+            for (int c = lane; c < ld2; c += G) {
+                double2 u = Ui[c], v = Vi[c];
+                a = fma(u.x, v.x, a);
+                a = fma(u.y, v.y, a);
+            }
+        }
+        a = group_sum<G>(a);
+        if (live && lane == 0) cv[t] = dval[t] * a;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  per-constraint gather  cv[t] = sum_e coef[e] * uvt[slot[e]]
+ *     reference: sdpDenseConeAUVImpl / sdpSparseConeAUVImpl -> sparseAUV / denseAUV,
+ *     lorads_sdp_conic.c:378-385,681-688 ; lorads_sdp_data.c:803-876,1017-1034
+ *     coef = 2a off the diagonal, a on it (the reference's "2 a UVt, halved on the diagonal").
+ * ------------------------------------------------------------------------------------------------*/
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_con_gather(int64_t mA, const int32_t *__restrict__ aptr,
+                                                         const int32_t *__restrict__ aslot,
+                                                         const double *__restrict__ acoef,
+                                                         const double *__restrict__ uvt, double *__restrict__ cv)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t iters = (mA + groups - 1) / groups;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t t = g0 + it * groups;
+        const bool live = t < mA;
+        double a = 0.0;
+        if (live) {
+            const int e0 = aptr[t], e1 = aptr[t + 1];
+            for (int e = e0 + lane; e < e1; e += G) a = fma(acoef[e], uvt[aslot[e]], a);
+        }
+        a = group_sum<G>(a);
+        if (live && lane == 0) cv[t] = a;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  S = [C] + sum_i w_i A_i on the pattern, as a GATHER over the slot-transposed CSR
+ *     reference: zeros + addObjCoeff + sdp*DataWeightSumImpl, lorads_sdp_conic.c:448-460,608-616,894-902
+ *     w is indexed by global constraint id (use_gid) or by the cone's compact id.
+ * ------------------------------------------------------------------------------------------------*/
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_wsum(int64_t nnzP, const int32_t *__restrict__ tptr,
+                                                   const int32_t *__restrict__ tidx, const double *__restrict__ tval,
+                                                   const double *__restrict__ w, const double *__restrict__ cval,
+                                                   int add_obj, double wscale, double *__restrict__ S)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t iters = (nnzP + groups - 1) / groups;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t k = g0 + it * groups;
+        const bool live = k < nnzP;
+        double a = 0.0;
+        if (live) {
+            const int e0 = tptr[k], e1 = tptr[k + 1];
+            for (int e = e0 + lane; e < e1; e += G) a = fma(wscale * w[tidx[e]], tval[e], a);
+        }
+        a = group_sum<G>(a);
+        if (live && lane == 0) S[k] = add_obj ? (cval[k] + a) : a;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  Y = alpha * S X + beta * Z   over the full symmetric CSR, S given on pattern slots
+ *     reference: dataMatSparseMultiRkMat / dataMatDenseMultiRkMat, lorads_sdp_data.c:750-763,948-973
+ *     One group of G lanes per row; each lane owns double2 column words c = lane + G*t.  Rows of X
+ *     are read as contiguous 16-byte words (row-major, ld multiple of 4).  With diag != nullptr the
+ *     operator is (S + Diag(diag)) X  (MaxCut-type A*(w) folded in without touching S).
+ * ------------------------------------------------------------------------------------------------*/
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_spmm(int64_t n, const int32_t *__restrict__ fptr,
+                                                   const int32_t *__restrict__ fcol, const int32_t *__restrict__ fslot,
+                                                   const double *__restrict__ S, const double *__restrict__ X, int ld,
+                                                   double alpha, double beta, const double *__restrict__ Z,
+                                                   double *__restrict__ Y)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    for (int64_t i = g0; i < n; i += groups) {
+        const int e0 = fptr[i], e1 = fptr[i + 1];
+        for (int cb = 0; cb < ld2; cb += G) {
+            const int c = cb + lane;
+            double2 acc = make_double2(0.0, 0.0);
+            if (c < ld2) {
+                int e = e0;
+                /* two entries per trip: more independent loads in flight */
+                for (; e + 1 < e1; e += 2) {
+                    const double s0 = S[fslot[e]], s1 = S[fslot[e + 1]];
+                    const double2 x0 = reinterpret_cast<const double2 *>(X + (size_t)fcol[e] * ld)[c];
+                    const double2 x1 = reinterpret_cast<const double2 *>(X + (size_t)fcol[e + 1] * ld)[c];
+                    acc.x = fma(s0, x0.x, acc.x);
+                    acc.y = fma(s0, x0.y, acc.y);
+                    acc.x = fma(s1, x1.x, acc.x);
+                    acc.y = fma(s1, x1.y, acc.y);
+                }
+                if (e < e1) {
+                    const double s0 = S[fslot[e]];
+                    const double2 x0 = reinterpret_cast<const double2 *>(X + (size_t)fcol[e] * ld)[c];
+                    acc.x = fma(s0, x0.x, acc.x);
+                    acc.y = fma(s0, x0.y, acc.y);
+                }
+                double2 o = make_double2(alpha * acc.x, alpha * acc.y);
+                if (Z != nullptr) {
+                    const double2 z = reinterpret_cast<const double2 *>(Z + (size_t)i * ld)[c];
+                    o.x = fma(beta, z.x, o.x);
+                    o.y = fma(beta, z.y, o.y);
+                }
+                reinterpret_cast<double2 *>(Y + (size_t)i * ld)[c] = o;
+            }
+        }
+    }
+}
+
+/* CG operator tail for diag_only cones: res = x + Diag(sum_t w_t a_t e_{d_t}) V, via a per-row
+ * accumulated diagonal `dg` (length n)          reference: linSysProduct, lorads_admm.c:471-486 */
+__global__ void __launch_bounds__(LGPU_TPB) k_rowscale_add(int64_t n, int ld, const double *__restrict__ dg,
+                                                           const double *__restrict__ V, const double *__restrict__ X,
+                                                           double *__restrict__ out)
+{
+    const int64_t total = n * (int64_t)ld;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t row = i / ld;
+        out[i] = fma(dg[row], V[i], X[i]);
+    }
+}
+
+/* host column-major n x r  <->  device row-major n x ld (padding columns zeroed) */
+__global__ void __launch_bounds__(LGPU_TPB) k_col2row(int64_t n, int r, int ld, const double *__restrict__ cm,
+                                                      double *__restrict__ rm)
+{
+    __shared__ double tile[32][33];
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    for (int c0 = 0; c0 < ld; c0 += 32) {
+        /* read: threads along rows (contiguous in column-major) */
+        for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+            const int64_t row = row0 + threadIdx.x;
+            const int col = c0 + cc;
+            tile[cc][threadIdx.x] = (row < n && col < r) ? cm[(size_t)col * n + row] : 0.0;
+        }
+        __syncthreads();
+        for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+            const int64_t row = row0 + rr;
+            const int col = c0 + threadIdx.x;
+            if (row < n && col < ld) rm[(size_t)row * ld + col] = tile[threadIdx.x][rr];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, const double *__restrict__ rm,
+                                                      double *__restrict__ cm)
+{
+    __shared__ double tile[32][33];
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    for (int c0 = 0; c0 < r; c0 += 32) {
+        for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+            const int64_t row = row0 + rr;
+            const int col = c0 + threadIdx.x;
+            tile[rr][threadIdx.x] = (row < n && col < r) ? rm[(size_t)row * ld + col] : 0.0;
+        }
+        __syncthreads();
+        for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+            const int64_t row = row0 + threadIdx.x;
+            const int col = c0 + cc;
+            if (row < n && col < r) cm[(size_t)col * n + row] = tile[threadIdx.x][cc];
+        }
+        __syncthreads();
+    }
+}
+
+/* re-stride a row-major factor from (r_old, ld_old) to ld_new and plant the AUG_RANK seed:
+ * new column r_old + j gets 1/sqrt(dr) at row j (j < min(n, dr))      lorads_solver.c:1096-1106,1180-1214 */
+__global__ void __launch_bounds__(LGPU_TPB) k_restride_aug(int64_t n, int r_old, int ld_old, int r_new, int ld_new,
+                                                           const double *__restrict__ src, double *__restrict__ dst,
+                                                           int plant)
+{
+    const int64_t total = n * (int64_t)ld_new;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int dr = r_new - r_old;
+    const double seed = dr > 0 ? 1.0 / sqrt((double)(n < dr ? n : dr)) : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t row = i / ld_new;
+        const int col = (int)(i - row * ld_new);
+        double v = 0.0;
+        if (col < r_old) v = src[(size_t)row * ld_old + col];
+        else if (plant && col < r_new && (int64_t)(col - r_old) == row) v = seed;
+        dst[i] = v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K12 r x r Gram of a tall factor (oracle rank)      reference: build_gram_from_factor/_average,
+ *     lorads_logging.c:216-270.  Tile (ti,tj) of 16x16 columns per block column, row chunks per block
+ *     row; partial tiles go to `part` and are summed in fixed order by k_gram_finish.
+ * ------------------------------------------------------------------------------------------------*/
+__global__ void __launch_bounds__(256) k_gram_partial(int64_t n, int r, int ld, const double *__restrict__ A,
+                                                      const double *__restrict__ B, int average, int64_t rows_per_chunk,
+                                                      double *__restrict__ part)
+{
+    __shared__ double sa[64][17], sb[64][17];
+    const int nt = (r + 15) / 16;
+    const int ti = blockIdx.y / nt, tj = blockIdx.y % nt;
+    const int a = threadIdx.x / 16, b2 = threadIdx.x % 16;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+    const int64_t r1 = (r0 + rows_per_chunk < n) ? r0 + rows_per_chunk : n;
+    double acc = 0.0;
+    for (int64_t base = r0; base < r1; base += 64) {
+        for (int q = threadIdx.x; q < 64 * 16; q += 256) {
+            const int rr = q / 16, cc = q % 16;
+            const int64_t row = base + rr;
+            const int ca = ti * 16 + cc, cb = tj * 16 + cc;
+            double va = 0.0, vb = 0.0;
+            if (row < r1) {
+                if (ca < r) va = average ? 0.5 * (A[(size_t)row * ld + ca] + B[(size_t)row * ld + ca]) : A[(size_t)row * ld + ca];
+                if (cb < r) vb = average ? 0.5 * (A[(size_t)row * ld + cb] + B[(size_t)row * ld + cb]) : A[(size_t)row * ld + cb];
+            }
+            sa[rr][cc] = va;
+            sb[rr][cc] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) acc = fma(sa[rr][a], sb[rr][b2], acc);
+        __syncthreads();
+    }
+    part[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 256 + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, int r, const double *__restrict__ part,
+                                                     double *__restrict__ gram)
+{
+    const int nt = (r + 15) / 16;
+    const int tile = blockIdx.x;
+    const int ti = tile / nt, tj = tile % nt;
+    const int a = threadIdx.x / 16, b2 = threadIdx.x % 16;
+    double t = 0.0;
+    for (int c = 0; c < nchunks; ++c) t += part[((size_t)c * ntile2 + tile) * 256 + threadIdx.x];
+    const int ca = ti * 16 + a, cb = tj * 16 + b2;
+    if (ca < r && cb < r) gram[(size_t)ca * r + cb] = t;
+}
+
+#endif
