@@ -145,11 +145,6 @@ int lgpu_op_wsum(lgpu_ctx *ctx, int cone, const double *w, int add_obj, double *
 int lgpu_op_wsum_mulrk(lgpu_ctx *ctx, int cone, int64_t r, const double *w, int add_obj, const double *X,
                        double *Y);
 
-/* ---- multi-GPU (row-block partition) --------------------------------------------*/
-/* ncclUniqueId is 128 bytes; rank 0 calls lgpu_nccl_unique_id and the host side distributes it. */
-int lgpu_nccl_unique_id(unsigned char id[128]);
-int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int rank, int world);
-
 #ifdef __cplusplus
 }
 #endif

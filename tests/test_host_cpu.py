@@ -1,0 +1,152 @@
+"""CPU: host-side logic of the drop-in (C reader, scalar line search, Jacobi eigenvalues, CLI) and the C-ABI
+surface: the library loads and exports every symbol include/lorads_b200.h declares.  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, ROOT, inst_path
+import lorads_oracle as orc
+
+
+def test_abi_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "lorads_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 40
+    L = ctypes.CDLL(built.LIB_PATH)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert b"sm_100a" in ctypes.c_char_p(ctypes.cast(L.lgpu_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()).value
+    built.lib()  # the binding's own signature table resolves too
+
+
+def test_library_is_sm100a_only(built):
+    out = subprocess.run(["cuobjdump", "--list-elf", built.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_c_reader_matches_oracle_reader(built, name):
+    p = built.read_sdpa(inst_path(name))
+    q = orc.read_sdpa(inst_path(name))
+    assert p.m == q.m and list(p.dims) == list(q.dims) and p.nlp == q.nlp
+    assert np.array_equal(p.b, q.b)
+    for k, blk in enumerate(q.blocks):
+        beg = p.mat_beg[k]
+        assert len(beg) == q.m + 2
+        for c in range(q.m + 1):
+            idx, val = p.mat_idx[k][beg[c]:beg[c + 1]], p.mat_elem[k][beg[c]:beg[c + 1]]
+            o = np.argsort(idx, kind="stable")
+            assert np.array_equal(idx[o], blk.cols_idx[c]) and np.array_equal(val[o], blk.cols_val[c]), (k, c)
+    if q.nlp:
+        obj = np.zeros(q.nlp)
+        obj[p.lp_idx[p.lp_beg[0]:p.lp_beg[1]]] = p.lp_elem[p.lp_beg[0]:p.lp_beg[1]]
+        assert np.array_equal(obj, q.lp_obj)
+        cols = [([], []) for _ in range(q.nlp)]
+        for c in range(q.m):
+            for e in range(p.lp_beg[c + 1], p.lp_beg[c + 2]):
+                cols[p.lp_idx[e]][0].append(c)
+                cols[p.lp_idx[e]][1].append(p.lp_elem[e])
+        for j in range(q.nlp):
+            assert np.array_equal(np.array(cols[j][0]), q.lp_cols[j][0])
+            assert np.array_equal(np.array(cols[j][1]), q.lp_cols[j][1])
+
+
+def test_reader_edge_cases(built, tmp_path):
+    # comments, braces/commas in the dims line, upper-triangular entries, tiny entries dropped, trailing comment block
+    f = tmp_path / "edge.dat-s"
+    f.write_text('"a comment\n* another\n2\n2\n{3, -2}\n1.0, 2.0\n'
+                 "0 1 1 2 0.5\n0 1 3 3 -1\n1 1 2 1 1.0\n1 1 1 1 1e-13\n2 1 3 3 2.0\n1 2 1 1 3.0\n2 2 2 2 -4.0\n0 2 2 2 7\n"
+                 "BEGIN.COMMENT\n9 9 9 9 9\n")
+    p = built.read_sdpa(str(f))
+    q = orc.read_sdpa(str(f))
+    assert p.m == 2 and list(p.dims) == [3] and p.nlp == 2
+    assert np.array_equal(p.b, [1.0, 2.0])
+    beg = p.mat_beg[0]
+    assert beg[-1] == 4  # the 1e-13 entry is dropped
+    for c in range(3):
+        assert np.array_equal(np.sort(p.mat_idx[0][beg[c]:beg[c + 1]]), q.blocks[0].cols_idx[c])
+    assert p.mat_elem[0][beg[0]:beg[1]].tolist() == [-0.5, 1.0]  # objective negated on read
+    # missing file: the binding raises, the binary exits 0 like the reference
+    with pytest.raises(built.LoradsError):
+        built.read_sdpa(str(tmp_path / "nope.dat-s"))
+    assert built.run_solver([str(tmp_path / "nope.dat-s")]).returncode == 0
+
+
+def test_line_search_matches_oracle(built):
+    H = built.host_lib()
+    rng = np.random.default_rng(7)
+    dp = ctypes.POINTER(ctypes.c_double)
+    for trial in range(2000):
+        rho = float(10 ** rng.uniform(-2, 3))
+        m = 6
+        lam, q0, q1, q2 = (rng.normal(size=m) for _ in range(4))
+        if trial % 7 == 0:
+            q2 *= 0.0  # degenerate quartic -> quadratic
+        p1, p2 = float(rng.normal()), float(rng.normal())
+        a, b, c, d = orc.line_search_coeffs(rho, lam, p1, p2, q0, q1, q2)
+        q0p = q0 + lam / rho
+        terms = np.array([p1, p2, q2 @ q2, q1 @ q2, q0p @ q2, q1 @ q1, q0p @ q1])
+        tau = ctypes.c_double(-7.0)
+        n = H.lh_line_search(rho, terms.ctypes.data_as(dp), ctypes.byref(tau))
+        try:
+            with np.errstate(all="ignore"):
+                on, otau = orc.line_search_tau(a, b, c, d)
+        except ZeroDivisionError:  # python raises where C yields inf/nan (0/0 in the degenerate cubic)
+            continue
+        assert n == on
+        if not (np.isnan(otau) or np.isnan(tau.value)):
+            assert abs(tau.value - otau) <= 1e-9 * max(1.0, abs(otau)), (trial, tau.value, otau)
+
+
+def test_cubic_equation(built):
+    H = built.host_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    for coef in [(1.0, -6.0, 11.0, -6.0), (2.0, 0.0, 1.0, -3.0), (4.0, 1.0, -2.0, 0.3), (1.0, -3.0, 3.0, -1.0)]:
+        res = np.zeros(3)
+        n = H.lh_cubic_equation(*coef, res.ctypes.data_as(dp))
+        on, ores = orc.cubic_equation(*coef)
+        assert n == on and np.allclose(res, ores, rtol=1e-13, atol=0)
+
+
+def test_jacobi_eigenvalues(built):
+    H = built.host_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 5, 14, 41):
+        A = rng.normal(size=(n + 3, n))
+        G = A.T @ A
+        w = np.zeros(n)
+        H.lh_sym_eigvals(n, G.copy().ctypes.data_as(dp), w.ctypes.data_as(dp))
+        assert np.allclose(w, np.linalg.eigvalsh(G), rtol=1e-10, atol=1e-12 * np.max(np.abs(G)))
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the product path must fail loudly (nonzero exit, message), never compute on the CPU."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(built.LoradsError, match="no CPU fallback"):
+        built.Context(0)
+    r = built.run_solver([inst_path("G11")])
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ltr-lowrank-sdp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".c", ".h", ".cu", ".cuh")) or fn == "Makefile":
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "lorads_oracle" not in txt and "oracle/" not in txt and "_ref" not in txt, fn
