@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- LoRADS ALM inner iterations per second on the C5 workload (BASELINE.json): synthetic random-graph
+MaxCut SDP, n = m = 10^7, average degree 10, rank 32, FP64.
+
+A "step" is ONE ALM inner iteration exactly as the reference sequences it (lorads_alm.c:1302-1378): L-BFGS
+direction, q1/q2/p1/p2 (two constraint-operator applications), exact quartic line search (scalar, on the host),
+R += tau D, gradient 2 (C + A^*(M1)) R, L-BFGS pair update, primal infeasibility from a fresh A(RR^T).
+
+  value      steps / device time of the timed region, problem and factors already resident in HBM (CUDA events on
+             the library's stream; the seven line-search scalars still travel to the host every step -- that is
+             part of the algorithm's critical path).
+  e2e        the same K steps through the public C ABI starting from HOST buffers: the initial factor goes
+             host (pinned) -> device inside the timed region, every step's scalars come back to the host, and
+             the final factor, dual vector and constraint values are read back to the host at the end.
+  roofline   dominant kernel class by summed device time (CUDA events around every launch, lgpu_profile_*):
+             algorithmic bytes per launch (DESIGN.md "Algorithmic bytes") / mean launch time vs the measured
+             HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference
+             the UNMODIFIED reference (oracle/_ref/liblorads_ref.so = its own objects, driven in main.c's order)
+             on a bounded sample of the same workload: same generator, degree and rank at n = 40000 (the largest
+             size the reference's INT32 build can index is 46340), its iterations/s scaled by n_sample / n
+             (every term of the iteration is linear in n at fixed degree and rank).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "ltr-lowrank-sdp_b200"))
+
+METRIC = "alm_inner_iters_per_sec"
+UNIT = "iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--out-degree", type=int, default=5)
+    ap.add_argument("--rank", type=int, default=32)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample-n", type=int, default=40000)
+    ap.add_argument("--cpu-sample-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config(args, world):
+    return {"workload": f"synthetic random-graph MaxCut SDP (BASELINE configs[4]): n=m={args.n}, avg degree "
+                        f"{2 * args.out_degree}, rank {args.rank}, seed {args.seed}, one ALM inner iteration per step",
+            "n": args.n, "rank": args.rank, "avg_degree": 2 * args.out_degree,
+            "partition": "single GPU" if world == 1 else f"row blocks over {world} GPUs",
+            "l2": "inputs larger than L2 (factor 8*n*r bytes >> 126 MB); no flush needed"}
+
+
+# ---- clocks --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- workload ------------------------------------------------------------------------------------------
+def build_problem(lb, n, out_degree, seed):
+    ei, ej, w = lb.random_graph(n, out_degree, seed)
+    return lb.maxcut_problem(n, ei, ej, w), len(ei)
+
+
+def line_search(H, rho, terms):
+    tau = ctypes.c_double(0.0)
+    H.lh_line_search(float(rho), terms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(tau))
+    return tau.value
+
+
+def alm_iteration(ctx, lb, H, rho, k):
+    """one pass of lorads_alm.c:1302-1378 through the C ABI; returns the scalars the host state machine reads"""
+    ctx.lbfgs_direction(k)
+    terms = ctx.alm_linesearch_terms(rho)
+    tau = line_search(H, rho, terms)
+    lag, pinf = ctx.alm_inner_update(rho, tau)
+    return tau, lag, pinf
+
+
+def algorithmic_bytes(cls, info, n, ld, m, nlaunch_per_step):
+    """compulsory HBM bytes of ONE launch of a kernel class on this workload (every operand once, outputs once,
+    int32 indices) -- DESIGN.md 'Algorithmic bytes'."""
+    F = 8.0 * n * ld
+    nnzP, nnzF = info["nnzP"], 2 * info["nnzP"] - n
+    if cls == "k_uvt":       # 3 launches / step: (R,D) reads two factors, (D,D) and (R,R) one
+        return 16.0 * nnzP + F * (4.0 / 3.0)
+    if cls == "k_spmm":
+        return 8.0 * nnzF + 8.0 * nnzP + 4.0 * (n + 1) + 2 * F
+    if cls == "k_mc_spmm":
+        return 12.0 * nnzF + 4.0 * (n + 1) + 3 * F + 16.0 * m
+    if cls == "k_mc_step":
+        return 10 * F + 56.0 * m
+    if cls == "k_mc_dir":    # five fused passes: 13 F read + 4 F written over 5 launches
+        return 17 * F / 5.0
+    if cls == "k_wsum":
+        return 12.0 * info["nnzA"] + 8.0 * m + 16.0 * nnzP
+    if cls == "k_gather":
+        return 12.0 * info["nnzA"] + 8.0 * nnzP + 8.0 * m
+    if cls in ("k_vec", "k_reduce"):
+        return None
+    return None
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- CPU baseline: the unmodified reference on a bounded sample -----------------------------------------
+def reference_rate(args, steps, warmup):
+    """iterations/s of the reference's own ALM inner iteration (oracle/_ref/liblorads_ref.so) on the sample, and
+    the figure scaled to the full workload."""
+    import lorads_b200 as lb
+    lib = os.path.join(ROOT, "oracle", "_ref", "liblorads_ref.so")
+    if not os.path.exists(lib):
+        return None
+    ns = min(args.cpu_sample_n, args.n)
+    p, _ = build_problem(lb, ns, args.out_degree, args.seed)
+    path = f"/tmp/lorads_bench_sample_{ns}.dat-s"
+    lb.write_sdpa(path, p)
+    L = ctypes.CDLL(lib)
+    L.rh_load.argtypes = [ctypes.c_char_p, ctypes.c_double, ctypes.c_int]
+    L.rh_alm_inner_iter.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.rh_alm_cal_grad.restype = ctypes.c_double
+    L.rh_alm_cal_grad.argtypes = [ctypes.c_double]
+    L.rh_rho0.restype = ctypes.c_double
+    devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        rc = L.rh_load(path.encode(), 2.0, args.rank)
+    finally:
+        os.dup2(saved, 1)
+    if rc != 0:
+        return None
+    rho = L.rh_rho0()
+    L.rh_init_constr_val_sum_RR()
+    L.rh_alm_cal_grad(rho)
+    sc = np.zeros(6)
+    scp = sc.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    k = 0
+    for _ in range(warmup):
+        L.rh_alm_inner_iter(rho, k, scp); k += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        L.rh_alm_inner_iter(rho, k, scp); k += 1
+    dt = time.perf_counter() - t0
+    rate = steps / dt
+    return {"sample_rate": rate, "scaled": rate * ns / args.n, "n_sample": ns, "seconds": dt, "steps": steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    r = reference_rate(args, max(args.steps, 1) * 2, args.warmup)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblorads_ref.so is not built"}))
+        return
+    sample = (f"unmodified reference objects (liblorads_ref.so), same generator/degree/rank at n={r['n_sample']} "
+              f"({r['steps']} ALM inner iterations in {r['seconds']:.1f} s = {r['sample_rate']:.3f} it/s), scaled by "
+              f"n_sample/n; the reference is single-threaded C (no OpenMP/pthreads; BLAS-1 calls of length 32 do not thread)")
+    line = {"impl": "reference", "metric": METRIC, "value": r["scaled"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": 1e3 / r["scaled"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args, 1),
+            "cpu_baseline": {"value": r["scaled"], "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+            "e2e": {"value": r["scaled"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---- our arm -------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import lorads_b200 as lb
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("row-block partitioned path: see bench_multi in DESIGN.md (not wired in this build)")
+    torch.cuda.set_device(local)
+    H = lb.host_lib()
+    n, r = args.n, args.rank
+    t0 = time.perf_counter()
+    p, nedges = build_problem(lb, n, args.out_degree, args.seed)
+    t_gen = time.perf_counter() - t0
+    ctx = lb.Context(local)
+    t0 = time.perf_counter()
+    ctx.load(p)
+    t_upload = time.perf_counter() - t0
+    info = ctx.cone_info(0)
+    ctx.alloc_vars([r], 2)
+    ld = (r + 3) // 4 * 4
+    # seeded host initial point in pinned memory (the reference's rand()/RAND_MAX - rand()/RAND_MAX distribution)
+    rng = np.random.default_rng(925)
+    R0 = torch.empty((r, n), dtype=torch.float64, pin_memory=True)   # column-major n x r
+    R0np = R0.numpy()
+    for c in range(r):
+        R0np[c] = rng.random(n) - rng.random(n)
+    R0f = R0np.T  # (n, r) Fortran-ordered view of the pinned buffer
+    rho = 1.0 / np.sqrt(n)
+    Rout = torch.empty((r, n), dtype=torch.float64, pin_memory=True)
+
+    def start(from_host):
+        if from_host:
+            ctx.set_factor(lb.R, 0, R0f)
+        ctx.set_vec(lb.VEC_DUAL, np.zeros(n))
+        ctx.init_constr_val(lb.PAIR_RR)
+        ctx.alm_cal_grad(rho)
+
+    # ---- device-resident timing -------------------------------------------------------------------------
+    start(True)
+    k = 0
+    for _ in range(args.warmup):
+        alm_iteration(ctx, lb, H, rho, k); k += 1
+    ctx.sync()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = ctx.launch_count
+    ctx.timer_record(0)
+    for _ in range(args.steps):
+        out = alm_iteration(ctx, lb, H, rho, k); k += 1
+    ctx.timer_record(1)
+    ctx.sync()
+    ms = ctx.timer_elapsed_ms(0, 1)
+    launches = ctx.launch_count - l0
+    clk = clocks.stop()
+    value = args.steps / (ms * 1e-3)
+
+    # ---- per-class launch times over another K steps (same loop, events around every launch) ---------------
+    ctx.profile_enable(True)
+    for _ in range(args.steps):
+        alm_iteration(ctx, lb, H, rho, k); k += 1
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    tot = sum(v[0] for v in prof.values()) or 1.0
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    peak, peak_src = peaks()
+    per_launch_ms = dom[1][0] / max(dom[1][1], 1)
+    ab = algorithmic_bytes(dom[0], info, n, ld, n, dom[1][1] / args.steps)
+    roof = {"bound": "hbm", "kernel": dom[0], "share_of_step": dom[1][0] / tot, "launches_per_step": dom[1][1] / args.steps,
+            "ms_per_launch": per_launch_ms, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
+            "classes": {kname: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                        for kname, v in prof.items() if v[1]}}
+    if ab is not None:
+        roof["algorithmic_bytes_per_launch"] = ab
+        roof["achieved"] = ab / (per_launch_ms * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+    else:
+        roof["achieved"] = None
+        roof["frac"] = None
+
+    # ---- end to end from host buffers ----------------------------------------------------------------------
+    ctx.sync()
+    t0 = time.perf_counter()
+    start(True)
+    for kk in range(args.steps):
+        alm_iteration(ctx, lb, H, rho, kk)
+    Rfin = ctx.get_factor(lb.R, 0)
+    lam = ctx.get_vec(lb.VEC_DUAL)
+    cvs = ctx.get_vec(lb.VEC_CONSTR_SUM)
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    h2d = (8.0 * n * r + 8.0 * n) / args.steps
+    d2h = (8.0 * n * r + 16.0 * n) / args.steps + 9 * 8
+    assert np.isfinite(Rfin).all() and np.isfinite(out[2])
+    e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "note": "initial factor host->device, K iterations via the C ABI with the line search on the host, final "
+                   "factor + dual + constraint values device->host; transfer bytes amortised over the K steps"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config(args, world), "clocks": clk, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roof,
+            "setup_s": {"generate": t_gen, "preprocess_upload": t_upload},
+            "last_step": {"tau": out[0], "grad_norm_sq": out[1], "pinf": out[2]}}
+    if not args.no_cpu_baseline:
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+        cb = reference_rate(args, args.cpu_sample_steps, 2)
+        if cb is not None:
+            line["cpu_baseline"] = {"value": cb["scaled"], "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": f"unmodified reference (liblorads_ref.so) at n={cb['n_sample']}, same degree/rank: "
+                                              f"{cb['steps']} iterations in {cb['seconds']:.1f} s = {cb['sample_rate']:.3f} it/s, "
+                                              f"scaled by n_sample/n"}
+    ctx.close()
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

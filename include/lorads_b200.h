@@ -47,6 +47,17 @@ const char *lgpu_version(void);
 /* number of kernels this context has launched since creation (bench.py "gpu_launches") */
 int64_t lgpu_launch_count(const lgpu_ctx *ctx);
 
+/* ---- timing hooks (no reference counterpart; bench.py times on the library's own stream with these) ----*/
+int lgpu_sync(lgpu_ctx *ctx);
+/* CUDA events on the launching stream: record into slot 0..7, elapsed between two recorded slots */
+int lgpu_timer_record(lgpu_ctx *ctx, int slot);
+int lgpu_timer_elapsed_ms(lgpu_ctx *ctx, int slot_a, int slot_b, double *ms);
+/* per-launch device time by kernel class (CUDA events around every launch while enabled) */
+int lgpu_profile_enable(lgpu_ctx *ctx, int on);
+int lgpu_profile_read(lgpu_ctx *ctx, int ncls, double *ms, int64_t *count);
+int lgpu_profile_num_classes(void);
+const char *lgpu_profile_class_name(int cls);
+
 /* ---- problem upload (once) -------------------------------------------------------------------
  * Replaces LORADSInitSolver/LORADSSetDualObjective/LORADSInitConeData/LORADSPreprocess
  * (main.c:395-403; AConeProcData + AConePresolveData, lorads_sdp_conic.c:1046,1185-1393).
@@ -78,6 +89,13 @@ int lgpu_obj_scale(lgpu_ctx *ctx, double s);
  * M2temp, bLinSys, CG work vectors, L-BFGS ring of `lbfgs_len` (s,y) pairs, all m-vectors.  Values
  * are zero until set. */
 int lgpu_alloc_vars(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len);
+/* When the problem is one SDP block whose constraints are all single diagonal entries (MaxCut-type: diag(X) = b)
+ * and there is no LP block, the library runs a fused path: A(UV^T) is row-local, <C, UV^T> = <U, C V>, and
+ * (C + A^*(w)) X = C X + Diag(.) X, so an ALM inner iteration costs ONE sparse product.  Results agree with the
+ * general path to rounding.  This switch (default 1) exists for A/B parity tests; it takes effect at the next
+ * lgpu_alloc_vars / lgpu_aug_rank.  lgpu_uses_fused_path reports what the current variables use. */
+int lgpu_set_fused_path(lgpu_ctx *ctx, int on);
+int lgpu_uses_fused_path(const lgpu_ctx *ctx);
 int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double *colmajor);
 int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *colmajor);
 int lgpu_set_lp(lgpu_ctx *ctx, int which, const double *v);
@@ -104,6 +122,10 @@ int lgpu_lbfgs_direction(lgpu_ctx *ctx, int64_t inner_iter);
 int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7]);
 /* setAsNegGrad; ALMupdateVar (R += tau D); constrValSum += tau q1 + tau^2 q2 (lorads_alm.c:1342-1353) */
 int lgpu_alm_step(lgpu_ctx *ctx, double tau);
+/* the four calls above + below in one: setAsNegGrad, ALMupdateVar, constrValSum update, ALMCalGrad, setlbfgsHisTwo,
+ * updateDimacsALM (lorads_alm.c:1342-1357) -- what the host loop calls after the line search.  Returns
+ * sum |Grad|^2 and |b - A(RR^T)|_2 / (1 + |b|_1). */
+int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, double *lag_norm_square, double *pinf_l1);
 /* setlbfgsHisTwo (lorads_alm.c:842-890): s = tau D, y += Grad, beta = 1/<y,s>, advance the ring */
 int lgpu_lbfgs_push(lgpu_ctx *ctx, double tau);
 /* updateDimacsALM -> primalInfeasibility[LP] (lorads_alg_common.c:386-407): recompute A(RR^T) and

@@ -187,9 +187,12 @@ static int inner_step(lh_params *p, lh_solver *S, lh_alm_state *st, int64_t clea
     *tau_out = tau;
     if (nroot == 0) return 1;
     if (fabs(tau) < p->endTauTol) return 2;
-    if (lgpu_alm_step(S->gpu, tau) != 0) return -1;
-    if (lgpu_alm_cal_grad(S->gpu, st->rho, lag_out) != 0) return -1;
-    if (lgpu_lbfgs_push(S->gpu, tau) != 0) return -1;
+    /* step, gradient, L-BFGS pair and the fresh A(RR^T) in one device call; the infeasibility it returns is what
+     * updateDimacsALM would compute next (lorads_alm.c:1357) */
+    double pinf = 0.0;
+    if (lgpu_alm_inner_update(S->gpu, st->rho, tau, lag_out, &pinf) != 0) return -1;
+    S->dimacConstrVio = pinf;
+    S->dimacGap = fabs(S->pObjVal - S->dObjVal) / (1 + fabs(S->pObjVal) + fabs(S->dObjVal));
     return 0;
 }
 
@@ -250,8 +253,7 @@ int lh_alm_optimize(lh_params *p, lh_solver *S, lh_alm_state *st, double timeSol
                         tiny_tau = 1;
                         break;
                     }
-                    if (dimacs_alm(S)) return LH_RET_DEVICE;
-                    st->l_1_primal_infeasibility = S->dimacConstrVio;
+                    st->l_1_primal_infeasibility = S->dimacConstrVio; /* set by inner_step */
                     st->l_inf_primal_infeasibility = linf_from_l1(S, st->l_1_primal_infeasibility);
                     if (st->l_inf_primal_infeasibility <= p->phase1Tol && (st->primal_dual_gap <= p->phase1Tol || !p->highAccMode)) {
                         st->outerIter = k;
@@ -393,8 +395,7 @@ int lh_alm_optimize_reopt(lh_params *p, lh_solver *S, lh_alm_state *st, int earl
                         break;
                     }
                     cert_val = sqrt(lag) / (1 + S->cObjNrmInf);
-                    if (dimacs_alm(S)) return LH_RET_DEVICE;
-                    st->l_1_primal_infeasibility = S->dimacConstrVio;
+                    st->l_1_primal_infeasibility = S->dimacConstrVio; /* set by inner_step */
                     st->l_inf_primal_infeasibility = linf_from_l1(S, st->l_1_primal_infeasibility);
                     st->innerIter++; localIter++; cur_iter_counter++; clearLBFGS++;
                     if (localIter > 800) break;

@@ -82,26 +82,63 @@ static inline int grid_for(const lgpu_ctx *ctx, int64_t threads_needed)
     return (int)blocks;
 }
 
+/* live timing of one launch: CUDA events on the launching stream around the kernel (only when enabled) */
+static void prof_flush(lgpu_ctx *ctx)
+{
+    if (ctx->prof_recs.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ctx->prof_ms[r.cls] += (double)ms;
+            ctx->prof_cnt[r.cls] += 1;
+        }
+        ctx->prof_free.push_back(r.a);
+        ctx->prof_free.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+}
+struct Prof {
+    lgpu_ctx *ctx;
+    cudaEvent_t b = nullptr;
+    Prof(lgpu_ctx *c, int cls) : ctx(c)
+    {
+        ctx->launches++;
+        if (!ctx->prof) return;
+        if (ctx->prof_recs.size() >= 16384) prof_flush(ctx);
+        cudaEvent_t ev[2];
+        for (int k = 0; k < 2; ++k) {
+            if (!ctx->prof_free.empty()) { ev[k] = ctx->prof_free.back(); ctx->prof_free.pop_back(); }
+            else cudaEventCreate(&ev[k]);
+        }
+        cudaEventRecord(ev[0], ctx->stream);
+        b = ev[1];
+        ctx->prof_recs.push_back({cls, ev[0], ev[1]});
+    }
+    ~Prof() { if (b) cudaEventRecord(b, ctx->stream); }
+};
+
 template <class F>
 static void launch_map(lgpu_ctx *ctx, int64_t n, F f)
 {
     if (n <= 0) return;
+    Prof pr(ctx, KC_VEC);
     k_map<<<grid_for(ctx, n), LGPU_TPB, 0, ctx->stream>>>(n, f);
-    ctx->launches++;
 }
 template <int K, class F>
 static void launch_reduce(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec)
 {
+    Prof pr(ctx, KC_REDUCE);
     k_reduce<K><<<grid_for(ctx, n > 0 ? n : 1), LGPU_TPB, 0, ctx->stream>>>(n, f, ctx->partials, ctx->counter, ctx->dsc, spec);
-    ctx->launches++;
 }
 template <class F>
 static void launch_scalar(lgpu_ctx *ctx, F f)
 {
+    Prof pr(ctx, KC_SCALAR);
     k_scalar<<<1, 32, 0, ctx->stream>>>(f);
-    ctx->launches++;
 }
-static SlotSpec<1> slot1(int s, int acc = 0)
+static SlotSpec<1> slot1(int s, int acc = 0);
+static SlotSpec<1> slot1(int s, int acc)
 {
     SlotSpec<1> sp;
     sp.slot[0] = s;
@@ -145,18 +182,18 @@ static void run_uvt(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *U, cons
 {
     const int G = pick_group(ld);
     const int same = (U == V) ? 1 : 0;
+    Prof pr(ctx, KC_UVT);
     DISPATCH_G(G, k_uvt<GG><<<grid_for(ctx, c.nnzP * GG), LGPU_TPB, 0, ctx->stream>>>(
                       c.nnzP, c.pat_row, c.pat_col, U, V, (int)ld, same, out));
-    ctx->launches++;
 }
 /* cv = A_c(uvt) (compact, per non-zero constraint) */
 static void run_con_gather(lgpu_ctx *ctx, DevCone &c, const double *uvt, double *cv)
 {
     if (c.mA == 0) return;
     const int G = pick_list_group((double)c.nnzA / (double)c.mA);
+    Prof pr(ctx, KC_GATHER);
     DISPATCH_G(G, k_con_gather<GG><<<grid_for(ctx, c.mA * GG), LGPU_TPB, 0, ctx->stream>>>(
                       c.mA, c.a_ptr, c.a_slot, c.a_coef, uvt, cv));
-    ctx->launches++;
 }
 /* <C, uvt> accumulated into dsc[slot] */
 static void run_obj_gather(lgpu_ctx *ctx, DevCone &c, const double *uvt, int slot, int accumulate)
@@ -171,18 +208,18 @@ static void run_wsum(lgpu_ctx *ctx, DevCone &c, const double *w, bool w_global, 
 {
     const int G = pick_list_group(c.nnzP > 0 ? (double)c.nnzA / (double)c.nnzP : 0.0);
     const int32_t *tidx = w_global ? c.t_gid : c.t_loc;
+    Prof pr(ctx, KC_WSUM);
     DISPATCH_G(G, k_wsum<GG><<<grid_for(ctx, c.nnzP * GG), LGPU_TPB, 0, ctx->stream>>>(
                       c.nnzP, c.t_ptr, tidx, c.t_val, w, c.cval, add_obj ? 1 : 0, wscale, S));
-    ctx->launches++;
 }
 /* Y = alpha S X + beta Z */
 static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, const double *X, double alpha, double beta,
                      const double *Z, double *Y)
 {
     const int G = pick_group(ld);
+    Prof pr(ctx, KC_SPMM);
     DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, c.f_ptr, c.f_col, c.f_slot, S, X, (int)ld, alpha, beta, Z, Y));
-    ctx->launches++;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -237,18 +274,75 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     return 0;
 }
 
+/* ---- timing / profiling hooks (bench.py) ----------------------------------------------------------*/
+extern "C" int lgpu_sync(lgpu_ctx *ctx)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_timer_record(lgpu_ctx *ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= 8) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->timers[slot]) CU(ctx, cudaEventCreate(&ctx->timers[slot]));
+    CU(ctx, cudaEventRecord(ctx->timers[slot], ctx->stream));
+    return 0;
+}
+extern "C" int lgpu_timer_elapsed_ms(lgpu_ctx *ctx, int a, int b, double *ms)
+{
+    if (!ctx || a < 0 || a >= 8 || b < 0 || b >= 8 || !ctx->timers[a] || !ctx->timers[b]) return 1;
+    CU(ctx, cudaEventSynchronize(ctx->timers[b]));
+    float f = 0.f;
+    CU(ctx, cudaEventElapsedTime(&f, ctx->timers[a], ctx->timers[b]));
+    *ms = (double)f;
+    return 0;
+}
+extern "C" int lgpu_profile_enable(lgpu_ctx *ctx, int on)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    prof_flush(ctx);
+    for (int k = 0; k < KC_COUNT; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_cnt[k] = 0; }
+    ctx->prof = on != 0;
+    return 0;
+}
+extern "C" int lgpu_profile_read(lgpu_ctx *ctx, int ncls, double *ms, int64_t *count)
+{
+    if (!ctx) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    prof_flush(ctx);
+    for (int k = 0; k < ncls; ++k) {
+        ms[k] = k < KC_COUNT ? ctx->prof_ms[k] : 0.0;
+        count[k] = k < KC_COUNT ? ctx->prof_cnt[k] : 0;
+    }
+    return 0;
+}
+extern "C" int lgpu_profile_num_classes(void) { return KC_COUNT; }
+extern "C" const char *lgpu_profile_class_name(int cls)
+{
+    static const char *names[KC_COUNT] = {"k_uvt", "k_gather", "k_wsum", "k_spmm", "k_vec", "k_reduce", "k_scalar",
+                                          "k_layout", "k_mc_spmm", "k_mc_step", "k_mc_dir"};
+    return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
+}
+
 static void free_cone(DevCone &c)
 {
     dev_free(c.pat_row); dev_free(c.pat_col); dev_free(c.cval); dev_free(c.c_slot); dev_free(c.c_coef);
     dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid);
     dev_free(c.t_ptr); dev_free(c.t_loc); dev_free(c.t_gid); dev_free(c.t_val);
     dev_free(c.f_ptr); dev_free(c.f_col); dev_free(c.f_slot); dev_free(c.d_row); dev_free(c.d_val);
+    dev_free(c.mc_val); dev_free(c.rc_ptr); dev_free(c.rc_gid); dev_free(c.rc_a);
     dev_free(c.uvt); dev_free(c.S); dev_free(c.cv); dev_free(c.wtmp);
 }
 static void free_vars(lgpu_ctx *ctx)
 {
     dev_free(ctx->R); dev_free(ctx->U); dev_free(ctx->V); dev_free(ctx->G); dev_free(ctx->M2); dev_free(ctx->bLin);
     dev_free(ctx->cg_r); dev_free(ctx->cg_p); dev_free(ctx->cg_Q); dev_free(ctx->stage);
+    dev_free(ctx->CR); dev_free(ctx->CD);
+    ctx->cr_valid = ctx->cd_valid = false;
+    ctx->mc = false;
     for (auto &p : ctx->s) dev_free(p);
     for (auto &p : ctx->y) dev_free(p);
     ctx->s.clear();
@@ -268,6 +362,9 @@ extern "C" void lgpu_destroy(lgpu_ctx *ctx)
     dev_free(ctx->lp.obj); dev_free(ctx->lp.r_ptr); dev_free(ctx->lp.r_col); dev_free(ctx->lp.r_val);
     dev_free(ctx->lp.c_ptr); dev_free(ctx->lp.c_row); dev_free(ctx->lp.c_val); dev_free(ctx->lp.nrm2sq);
     dev_free(ctx->dsc); dev_free(ctx->partials); dev_free(ctx->counter);
+    prof_flush(ctx);
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
+    for (auto &e : ctx->timers) if (e) cudaEventDestroy(e);
     if (ctx->hsc) cudaFreeHost(ctx->hsc);
     if (ctx->hstage) cudaFreeHost(ctx->hstage);
     if (ctx->dstage) cudaFree(ctx->dstage);
@@ -552,6 +649,25 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     if (diag_only) {
         TRY(dev_upload(ctx, &c.d_row, d_row));
         TRY(dev_upload(ctx, &c.d_val, d_val));
+        /* fused path layout: C's value per full-CSR entry; row -> constraints, stable in constraint order */
+        std::vector<double> mc_val(c.nnzF);
+        for (int64_t e = 0; e < c.nnzF; ++e) mc_val[e] = cval[f_slot[e]];
+        std::vector<int32_t> rc_ptr(n + 1, 0), rc_gid(mA);
+        std::vector<double> rc_a(mA);
+        for (int64_t t = 0; t < mA; ++t) rc_ptr[d_row[t] + 1]++;
+        for (int64_t i = 0; i < n; ++i) rc_ptr[i + 1] += rc_ptr[i];
+        {
+            std::vector<int32_t> fill(rc_ptr.begin(), rc_ptr.end() - 1);
+            for (int64_t t = 0; t < mA; ++t) {
+                const int32_t q = fill[d_row[t]]++;
+                rc_gid[q] = con_gid[t];
+                rc_a[q] = d_val[t];
+            }
+        }
+        TRY(dev_upload(ctx, &c.mc_val, mc_val));
+        TRY(dev_upload(ctx, &c.rc_ptr, rc_ptr));
+        TRY(dev_upload(ctx, &c.rc_gid, rc_gid));
+        TRY(dev_upload(ctx, &c.rc_a, rc_a));
     }
     TRY(dev_alloc(ctx, &c.uvt, (size_t)nnzP));
     TRY(dev_alloc(ctx, &c.S, (size_t)nnzP));
@@ -682,6 +798,10 @@ extern "C" int lgpu_obj_scale(lgpu_ctx *ctx, double s)
         double *cv = c.cval, *cc = c.c_coef;
         launch_map(ctx, c.nnzP, [=] __device__(int64_t i) { cv[i] *= s; });
         launch_map(ctx, c.nnzC, [=] __device__(int64_t i) { cc[i] *= s; });
+        if (c.mc_val) {
+            double *mv = c.mc_val;
+            launch_map(ctx, c.nnzF, [=] __device__(int64_t i) { mv[i] *= s; });
+        }
         c.c_nrm1 *= fabs(s);
         c.c_nrm2sq *= s * s;
         c.c_nrminf *= fabs(s);
@@ -693,6 +813,7 @@ extern "C" int lgpu_obj_scale(lgpu_ctx *ctx, double s)
     }
     double *lam = ctx->lam;
     launch_map(ctx, ctx->m, [=] __device__(int64_t i) { lam[i] *= s; });
+    ctx->cr_valid = ctx->cd_valid = false;
     CHECK_LAUNCH(ctx);
     return 0;
 }
@@ -723,6 +844,14 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     ctx->N = off;
     double **flat[] = {&ctx->R, &ctx->U, &ctx->V, &ctx->G, &ctx->M2, &ctx->bLin, &ctx->cg_r, &ctx->cg_p, &ctx->cg_Q, &ctx->stage};
     for (auto p : flat) TRY(alloc_flat(ctx, p));
+    ctx->mc = ctx->fast_enabled && ctx->ncones == 1 && ctx->lp.n == 0 && ctx->cones[0].diag_only &&
+              ctx->cones[0].mA == ctx->m;
+    ctx->cr_valid = ctx->cd_valid = false;
+    ctx->cr_updates = 0;
+    if (ctx->mc) {
+        TRY(alloc_flat(ctx, &ctx->CR));
+        TRY(alloc_flat(ctx, &ctx->CD));
+    }
     ctx->h = lbfgs_len;
     ctx->head = 0;
     ctx->s.assign(lbfgs_len, nullptr);
@@ -734,6 +863,15 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     ctx->vars_ready = true;
     return 0;
 }
+
+/* A/B switch for the fused MaxCut-type path (default on); takes effect at the next lgpu_alloc_vars / lgpu_aug_rank */
+extern "C" int lgpu_set_fused_path(lgpu_ctx *ctx, int on)
+{
+    if (!ctx) return 1;
+    ctx->fast_enabled = on != 0;
+    return 0;
+}
+extern "C" int lgpu_uses_fused_path(const lgpu_ctx *ctx) { return (ctx && ctx->mc) ? 1 : 0; }
 
 extern "C" int lgpu_alloc_vars(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
 {
@@ -775,27 +913,30 @@ static double *mvec_of(lgpu_ctx *ctx, int which)
 static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *cm, double *dst)
 {
     const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
-    TRY(ensure_stage(ctx, bytes));
-    memcpy(ctx->hstage, cm, bytes);
-    CU(ctx, cudaMemcpyAsync(ctx->dstage, ctx->hstage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    /* straight from the caller's buffer: a pinned buffer goes by DMA, a pageable one is staged by the runtime */
+    TRY(ensure_dstage(ctx, bytes));
+    CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
     dim3 blk(32, 8);
-    k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, dst);
-    ctx->launches++;
+    {
+        Prof pr(ctx, KC_LAYOUT);
+        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, dst);
+    }
     CHECK_LAUNCH(ctx);
-    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* hstage is reused by the caller's next transfer */
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* the caller may reuse its buffer as soon as this returns */
     return 0;
 }
 static int download_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *src, double *cm)
 {
     const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
-    TRY(ensure_stage(ctx, bytes));
+    TRY(ensure_dstage(ctx, bytes));
     dim3 blk(32, 8);
-    k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage);
-    ctx->launches++;
+    {
+        Prof pr(ctx, KC_LAYOUT);
+        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage);
+    }
     CHECK_LAUNCH(ctx);
-    CU(ctx, cudaMemcpyAsync(ctx->hstage, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(cm, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(cm, ctx->hstage, bytes);
     return 0;
 }
 
@@ -804,6 +945,8 @@ extern "C" int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double 
     if (!ctx || !ctx->vars_ready || cone < 0 || cone >= ctx->ncones || !flat_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     DevCone &c = ctx->cones[cone];
+    if (which == LGPU_R) ctx->cr_valid = false;
+    if (which == LGPU_U) ctx->cd_valid = false;
     return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off);
 }
 extern "C" int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *cm)
@@ -856,6 +999,8 @@ extern "C" int lgpu_fill_factor_random(lgpu_ctx *ctx, int which, uint64_t seed)
 {
     if (!ctx || !ctx->vars_ready || !flat_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
+    if (which == LGPU_R) ctx->cr_valid = false;
+    if (which == LGPU_U) ctx->cd_valid = false;
     for (auto &c : ctx->cones) {
         double *p = flat_of(ctx, which) + c.off;
         const int64_t ld = c.ld, r = c.r;
@@ -901,9 +1046,9 @@ extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
     for (int w = 0; w < 4; ++w) {
         for (int c = 0; c < ctx->ncones; ++c) {
             DevCone &cn = ctx->cones[c];
+            Prof pr(ctx, KC_LAYOUT);
             k_restride_aug<<<grid_for(ctx, cn.n * cn.ld), LGPU_TPB, 0, ctx->stream>>>(
                 cn.n, (int)o_r[c], (int)o_ld[c], (int)cn.r, (int)cn.ld, olds[w] + o_off[c], news[w] + cn.off, 1);
-            ctx->launches++;
         }
         if (ctx->lp.n > 0)
             CU(ctx, cudaMemcpyAsync(news[w] + ctx->lp.off, olds[w] + o_lp_off, sizeof(double) * ctx->lp.n,
@@ -918,6 +1063,49 @@ extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
 /* ------------------------------------------------------------------------------------------------
  * A(UV^T) and friends
  * ------------------------------------------------------------------------------------------------*/
+/* ------------------------------------------------------------------------------------------------
+ * fused MaxCut-type path helpers (ctx->mc: one diag_only cone, every constraint non-zero, no LP)
+ * ------------------------------------------------------------------------------------------------*/
+/* out_k = scale a_k <A_i, B_i> ; with b != nullptr also dsc[SC_PINF] = sum (b - out)^2 */
+static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double scale, double *out, bool with_pinf)
+{
+    DevCone &c = ctx->cones[0];
+    const int G = pick_group(c.ld);
+    Prof pr(ctx, KC_GATHER);
+    DISPATCH_G(G, k_mc_rowdot<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.n, (int)c.ld, A, B, c.rc_ptr, c.rc_gid, c.rc_a, scale, out, with_pinf ? ctx->b : nullptr,
+                      ctx->partials, ctx->counter, ctx->dsc, slot1(SC_PINF, 0)));
+}
+/* T = C X (no epilogue) */
+static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
+{
+    DevCone &c = ctx->cones[0];
+    const int G = pick_group(c.ld);
+    SlotSpec<2> sp;
+    sp.slot[0] = SC_TMP; sp.slot[1] = SC_TMP2; sp.accumulate = 0;
+    Prof pr(ctx, KC_MC_SPMM);
+    DISPATCH_G(G, k_mc_spmm<GG, false><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.n, c.f_ptr, c.f_col, c.mc_val, X, (int)c.ld, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      ctx->partials, ctx->counter, ctx->dsc, sp));
+}
+static void mc_refresh_cr(lgpu_ctx *ctx)
+{
+    mc_spmm_plain(ctx, ctx->R, ctx->CR);
+    ctx->cr_valid = true;
+    ctx->cr_updates = 0;
+}
+/* Grad = 2 (CR + Diag(A^*(M1)) R), dsc[SC_LAG] = sum Grad^2 ; M1 already formed */
+static void mc_grad(lgpu_ctx *ctx)
+{
+    DevCone &c = ctx->cones[0];
+    if (!ctx->cr_valid) mc_refresh_cr(ctx);
+    const int G = pick_group(c.ld);
+    Prof pr(ctx, KC_MC_STEP);
+    DISPATCH_G(G, k_mc_grad<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+                      c.n, (int)c.ld, ctx->R, ctx->CR, ctx->G, c.rc_ptr, c.rc_gid, c.rc_a, ctx->M1, ctx->partials, ctx->counter,
+                      ctx->dsc, slot1(SC_LAG, 0)));
+}
+
 static void pair_ptrs(lgpu_ctx *ctx, int pair, double **A, double **B)
 {
     switch (pair) {
@@ -967,6 +1155,11 @@ extern "C" int lgpu_init_constr_val(lgpu_ctx *ctx, int pair)
     CU(ctx, cudaSetDevice(ctx->device));
     double *A, *B;
     pair_ptrs(ctx, pair, &A, &B);
+    if (ctx->mc) {
+        mc_rowdot(ctx, A, B, 1.0, ctx->cvs, false);
+        CHECK_LAUNCH(ctx);
+        return 0;
+    }
     cones_auv(ctx, A, B, -1);
     sum_constr_vals(ctx, A, B, 1.0, ctx->cvs);
     CHECK_LAUNCH(ctx);
@@ -1006,7 +1199,8 @@ extern "C" int lgpu_alm_cal_grad(lgpu_ctx *ctx, double rho, double *lag_norm_squ
         const double *lam = ctx->lam, *b = ctx->b, *cvs = ctx->cvs;
         launch_map(ctx, ctx->m, [=] __device__(int64_t i) { M1[i] = -lam[i] - rho * b[i] + rho * cvs[i]; });
     }
-    grad_from_m1(ctx);
+    if (ctx->mc) mc_grad(ctx);
+    else grad_from_m1(ctx);
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_LAG, 1));
     *lag_norm_square = ctx->hsc[SC_LAG];
@@ -1021,6 +1215,7 @@ extern "C" int lgpu_lbfgs_direction(lgpu_ctx *ctx, int64_t inner_iter)
     double *D = ctx->U;
     const double *G = ctx->G;
     double *dsc = ctx->dsc;
+    ctx->cd_valid = false;
     if (inner_iter == 0) {
         launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = -G[i]; });
         CHECK_LAUNCH(ctx);
@@ -1066,6 +1261,20 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     double *dsc = ctx->dsc;
+    if (ctx->mc) {
+        /* one sparse product T = C D with the q1/q2/p1/p2 epilogue */
+        DevCone &c = ctx->cones[0];
+        const int G = pick_group(c.ld);
+        SlotSpec<2> sp;
+        sp.slot[0] = SC_P1; sp.slot[1] = SC_P2; sp.accumulate = 0;
+        {
+            Prof pr(ctx, KC_MC_SPMM);
+            DISPATCH_G(G, k_mc_spmm<GG, true><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+                              c.n, c.f_ptr, c.f_col, c.mc_val, ctx->U, (int)c.ld, ctx->CD, ctx->R, c.rc_ptr, c.rc_gid, c.rc_a,
+                              ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, sp));
+        }
+        ctx->cd_valid = true;
+    } else {
     launch_scalar(ctx, [=] __device__() { dsc[SC_P1] = 0.0; dsc[SC_P2] = 0.0; });
     /* ALMCalq12p12: q1 = 2 A(sym(R D^T)), p1 = 2 <C, R D^T>; q2 = A(D D^T), p2 = <C, D D^T> */
     cones_auv(ctx, ctx->R, ctx->U, SC_P1);
@@ -1080,6 +1289,7 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
         launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * u[j], acc[0]); }, slot1(SC_P2, 1));
     }
     sum_constr_vals(ctx, ctx->U, ctx->U, 1.0, ctx->q2);
+    }
     {
         /* the five reductions of ALMLineSearch (lorads_alm.c:266-279); q0' = b - constrValSum + lambda / rho */
         const double *b = ctx->b, *cvs = ctx->cvs, *lam = ctx->lam, *q1 = ctx->q1, *q2 = ctx->q2;
@@ -1109,13 +1319,23 @@ extern "C" int lgpu_alm_step(lgpu_ctx *ctx, double tau)
 {
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
-    {
+    if (ctx->mc && ctx->cr_valid && ctx->cd_valid) {
+        double *yh = ctx->y[ctx->head], *R = ctx->R, *CR = ctx->CR;
+        const double *G = ctx->G, *D = ctx->U, *CD = ctx->CD;
+        launch_map(ctx, ctx->N, [=] __device__(int64_t i) {
+            yh[i] = -G[i];
+            R[i] = fma(tau, D[i], R[i]);
+            CR[i] = fma(tau, CD[i], CR[i]);
+        });
+        ctx->cr_updates++;
+    } else {
         double *yh = ctx->y[ctx->head], *R = ctx->R;
         const double *G = ctx->G, *D = ctx->U;
         launch_map(ctx, ctx->N, [=] __device__(int64_t i) {
             yh[i] = -G[i];
             R[i] = fma(tau, D[i], R[i]);
         });
+        ctx->cr_valid = false;
     }
     {
         double *cvs = ctx->cvs;
@@ -1148,9 +1368,56 @@ extern "C" int lgpu_lbfgs_push(lgpu_ctx *ctx, double tau)
     return 0;
 }
 
+/* Everything of one ALM inner iteration that follows the line search (lorads_alm.c:1342-1357):
+ * setAsNegGrad, ALMupdateVar, constrValSum update, ALMCalGrad, setlbfgsHisTwo, updateDimacsALM. */
+extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, double *lag_norm_square, double *pinf_l1)
+{
+    if (!ctx || !ctx->vars_ready) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!(ctx->mc && ctx->cr_valid && ctx->cd_valid)) {
+        TRY(lgpu_alm_step(ctx, tau));
+        TRY(lgpu_alm_cal_grad(ctx, rho, lag_norm_square));
+        TRY(lgpu_lbfgs_push(ctx, tau));
+        TRY(lgpu_primal_infeasibility(ctx, LGPU_PAIR_RR, pinf_l1));
+        return 0;
+    }
+    DevCone &c = ctx->cones[0];
+    const int G = pick_group(c.ld);
+    SlotSpec<3> sp;
+    sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
+    {
+        Prof pr(ctx, KC_MC_STEP);
+        DISPATCH_G(G, k_mc_step<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+                          c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[ctx->head], ctx->y[ctx->head],
+                          c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->partials,
+                          ctx->counter, ctx->dsc, sp));
+    }
+    double *dsc = ctx->dsc;
+    const int ib = SC_BETA0 + ctx->head;
+    launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
+    ctx->head = (ctx->head + 1) % ctx->h;
+    ctx->cr_updates++;
+    if (ctx->cr_updates >= 64) mc_refresh_cr(ctx); /* bound the rounding drift of the carried C R */
+    CHECK_LAUNCH(ctx);
+    TRY(fetch_scalars(ctx, SC_LAG, SC_YS - SC_LAG + 1));
+    *lag_norm_square = ctx->hsc[SC_LAG];
+    *pinf_l1 = sqrt(ctx->hsc[SC_PINF]) / (1.0 + ctx->b_nrm1);
+    return 0;
+}
+
 extern "C" int lgpu_primal_infeasibility(lgpu_ctx *ctx, int pair, double *pinf_l1)
 {
     if (!ctx || !ctx->vars_ready) return 1;
+    if (ctx->mc) {
+        CU(ctx, cudaSetDevice(ctx->device));
+        double *A, *B;
+        pair_ptrs(ctx, pair, &A, &B);
+        mc_rowdot(ctx, A, B, 1.0, ctx->cvs, true);
+        CHECK_LAUNCH(ctx);
+        TRY(fetch_scalars(ctx, SC_PINF, 1));
+        *pinf_l1 = sqrt(ctx->hsc[SC_PINF]) / (1.0 + ctx->b_nrm1);
+        return 0;
+    }
     TRY(lgpu_init_constr_val(ctx, pair));
     const double *b = ctx->b, *cvs = ctx->cvs;
     launch_reduce<1>(ctx, ctx->m, [=] __device__(int64_t i, double(&acc)[1]) {
@@ -1182,6 +1449,7 @@ extern "C" int lgpu_average_uv(lgpu_ctx *ctx)
     double *R = ctx->R;
     const double *U = ctx->U, *V = ctx->V;
     launch_map(ctx, ctx->N, [=] __device__(int64_t i) { R[i] = (U[i] + V[i]) / 2.0; });
+    ctx->cr_valid = false;
     CHECK_LAUNCH(ctx);
     return 0;
 }
@@ -1192,6 +1460,16 @@ extern "C" int lgpu_cal_obj(lgpu_ctx *ctx, int admm, double *pobj)
     CU(ctx, cudaSetDevice(ctx->device));
     if (admm) TRY(lgpu_average_uv(ctx));
     double *dsc = ctx->dsc;
+    if (ctx->mc) {
+        /* <C, R R^T> = <R, C R> */
+        if (!ctx->cr_valid) mc_refresh_cr(ctx);
+        const double *R = ctx->R, *CR = ctx->CR;
+        launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(R[i], CR[i], acc[0]); }, slot1(SC_OBJ));
+        CHECK_LAUNCH(ctx);
+        TRY(fetch_scalars(ctx, SC_OBJ, 1));
+        *pobj = ctx->hsc[SC_OBJ];
+        return 0;
+    }
     launch_scalar(ctx, [=] __device__() { dsc[SC_OBJ] = 0.0; });
     if (ctx->lp.n > 0) {
         const double *obj = ctx->lp.obj, *u = ctx->R + ctx->lp.off;
@@ -1225,6 +1503,7 @@ extern "C" int lgpu_alm_to_admm(lgpu_ctx *ctx)
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaMemcpyAsync(ctx->V, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->U, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->cd_valid = false;
     return 0;
 }
 extern "C" int lgpu_copy_r_to_v(lgpu_ctx *ctx)
@@ -1241,6 +1520,14 @@ extern "C" int lgpu_copy_r_to_v(lgpu_ctx *ctx)
 /* res = x + A_V^*(A_V(x)) V for cone c; x, fixed, res are row-major blocks of that cone */
 static void cg_mvec(lgpu_ctx *ctx, DevCone &c, const double *x, const double *fixed, double *res)
 {
+    if (ctx->mc) {
+        /* diagonal constraints: the whole operator is row-local, x_i + (sum_k a_k^2) <x_i, V_i> V_i */
+        const int G = pick_group(c.ld);
+        Prof pr(ctx, KC_MC_STEP);
+        DISPATCH_G(G, k_mc_cg_mvec<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(c.n, (int)c.ld, x, fixed, c.rc_ptr,
+                                                                                             c.rc_a, res));
+        return;
+    }
     /* LORADSUpdateConstrValCG: weight = A(sym(x V^T)) ; then w_sum = sum weight_i A_i ; res = w_sum V + x */
     run_uvt(ctx, c, c.ld, x, fixed, c.uvt);
     run_con_gather(ctx, c, c.uvt, c.wtmp);
@@ -1325,6 +1612,28 @@ static int admm_update_one(lgpu_ctx *ctx, int ci, double *upd_flat, const double
 {
     DevCone &c = ctx->cones[ci];
     const int64_t m = ctx->m;
+    if (ctx->mc) {
+        /* single cone: constrVal_c == constrValSum ; S V = C V + Diag(A^*(M1)) V */
+        double *M1 = ctx->M1;
+        const double *b = ctx->b, *cvs = ctx->cvs, *lam = ctx->lam;
+        launch_map(ctx, m, [=] __device__(int64_t i) { M1[i] = rho * ((-b[i] + cvs[i]) - cvs[i]) - lam[i]; });
+        double *upd = upd_flat, *M2 = ctx->M2, *bl = ctx->bLin;
+        const double *fixed = fixed_flat;
+        mc_spmm_plain(ctx, fixed, M2);
+        const int32_t *rp = c.rc_ptr, *rg = c.rc_gid;
+        const double *ra = c.rc_a;
+        const int64_t ld = c.ld;
+        launch_map(ctx, c.n * c.ld, [=] __device__(int64_t i) {
+            const int64_t row = i / ld;
+            double coef = 0.0;
+            for (int t = rp[row]; t < rp[row + 1]; ++t) coef = fma(M1[rg[t]], ra[t], coef);
+            const double m2 = fma(coef, fixed[i], M2[i]) - rho * fixed[i];
+            M2[i] = m2;
+            bl[i] = (-1.0 / rho) * m2;
+        });
+        TRY(cg_solve(ctx, ci, upd, fixed, bl, tol, maxit, iters));
+        return 0;
+    }
     {
         /* M1 = rho (-b + constrValSum - constrVal_c) - lambda */
         double *M1 = ctx->M1;
@@ -1352,6 +1661,10 @@ static int admm_update_one(lgpu_ctx *ctx, int ci, double *upd_flat, const double
 /* after a U- or V-update of cone c: constrValSum -= old cv ; cv = A(UV^T) ; constrValSum += cv */
 static void refresh_cone_cv(lgpu_ctx *ctx, DevCone &c)
 {
+    if (ctx->mc) {
+        mc_rowdot(ctx, ctx->U, ctx->V, 1.0, ctx->cvs, false);
+        return;
+    }
     const int32_t *gid = c.con_gid;
     double *cv = c.cv, *cvs = ctx->cvs;
     launch_map(ctx, c.mA, [=] __device__(int64_t t) { cvs[gid[t]] -= cv[t]; });
@@ -1408,6 +1721,7 @@ extern "C" int lgpu_admm_update_var(lgpu_ctx *ctx, double rho, double cg_tol, in
 {
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
+    ctx->cd_valid = false;
     for (int ci = 0; ci < ctx->ncones; ++ci) {
         DevCone &c = ctx->cones[ci];
         int64_t it = 0;
@@ -1443,9 +1757,14 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
     const double *A = (phase == 1 ? ctx->R : ctx->U) + c.off;
     const double *B = ctx->V + c.off;
     dim3 grid(nchunks, nt * nt);
-    k_gram_partial<<<grid, 256, 0, ctx->stream>>>(c.n, r, (int)c.ld, A, B, phase == 1 ? 0 : 1, rows_per_chunk, part);
-    k_gram_finish<<<nt * nt, 256, 0, ctx->stream>>>(nchunks, nt * nt, r, part, dg);
-    ctx->launches += 2;
+    {
+        Prof pr(ctx, KC_LAYOUT);
+        k_gram_partial<<<grid, 256, 0, ctx->stream>>>(c.n, r, (int)c.ld, A, B, phase == 1 ? 0 : 1, rows_per_chunk, part);
+    }
+    {
+        Prof pr(ctx, KC_LAYOUT);
+        k_gram_finish<<<nt * nt, 256, 0, ctx->stream>>>(nchunks, nt * nt, r, part, dg);
+    }
     CHECK_LAUNCH(ctx);
     CU(ctx, cudaMemcpyAsync(gram, dg, gram_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

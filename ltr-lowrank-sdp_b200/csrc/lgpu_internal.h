@@ -52,6 +52,27 @@ enum {
     SC_END = SC_LANCZOS + 8
 };
 
+/* kernel classes for the live per-launch timing (lgpu_profile_*), bench.py's roofline source */
+enum {
+    KC_UVT = 0,     /* k_uvt: pattern samples of sym(U V^T) */
+    KC_GATHER,      /* k_con_gather / objective gather / k_diag_auv */
+    KC_WSUM,        /* k_wsum: A^*(w) (+C) on the pattern */
+    KC_SPMM,        /* k_spmm: S X */
+    KC_VEC,         /* flat elementwise kernels */
+    KC_REDUCE,      /* flat fused elementwise + reduction kernels */
+    KC_SCALAR,      /* one-thread scalar kernels */
+    KC_LAYOUT,      /* transposes / re-stride / gram */
+    KC_MC_SPMM,     /* MaxCut-type fused: T = C D with q1/q2/p1/p2 epilogue */
+    KC_MC_STEP,     /* MaxCut-type fused: step + gradient + L-BFGS pair + A(RR^T) */
+    KC_MC_DIR,      /* fused two-loop passes */
+    KC_COUNT
+};
+
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+
 struct DevCone {
     /* sizes */
     int64_t n = 0;       /* block dimension */
@@ -80,6 +101,9 @@ struct DevCone {
     int32_t *t_ptr = nullptr, *t_loc = nullptr, *t_gid = nullptr; double *t_val = nullptr; /* by slot */
     int32_t *f_ptr = nullptr, *f_col = nullptr, *f_slot = nullptr; /* full CSR */
     int32_t *d_row = nullptr; double *d_val = nullptr; /* diag_only: row and value per constraint */
+    /* diag_only fused path: C per full-CSR entry, and row -> constraints (global id, a_k) */
+    double *mc_val = nullptr;
+    int32_t *rc_ptr = nullptr, *rc_gid = nullptr; double *rc_a = nullptr;
     /* scratch */
     double *uvt = nullptr;  /* [nnzP] */
     double *S = nullptr;    /* [nnzP] aggregate values (sdp_obj_sum / sdp_coeff_w_sum / slack) */
@@ -127,6 +151,12 @@ struct lgpu_ctx {
     bool vars_ready = false;
     double *R = nullptr, *U = nullptr, *V = nullptr, *G = nullptr, *M2 = nullptr, *bLin = nullptr,
            *cg_r = nullptr, *cg_p = nullptr, *cg_Q = nullptr, *stage = nullptr;
+    /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */
+    bool fast_enabled = true;
+    bool mc = false;
+    double *CR = nullptr, *CD = nullptr;
+    bool cr_valid = false, cd_valid = false;
+    int cr_updates = 0;
     int h = 0, head = 0;
     std::vector<double *> s, y;
     std::vector<int64_t> cg_last_iter; /* per cone: cg->iter persists across calls (reference quirk) */
@@ -136,6 +166,13 @@ struct lgpu_ctx {
     double *hsc = nullptr;      /* pinned host mirror */
     double *partials = nullptr; /* [8 * LGPU_MAX_PARTIAL_BLOCKS] */
     unsigned int *counter = nullptr;
+    /* live per-launch timing */
+    bool prof = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[KC_COUNT] = {0};
+    int64_t prof_cnt[KC_COUNT] = {0};
+    cudaEvent_t timers[8] = {nullptr};
     /* generic staging for host<->device operator calls */
     double *hstage = nullptr; size_t hstage_bytes = 0;
     void *dstage = nullptr; size_t dstage_bytes = 0;

@@ -436,4 +436,274 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
     if (ca < r && cb < r) gram[(size_t)ca * r + cb] = t;
 }
 
+/* ================================================================================================
+ * Fused path for cones whose constraints are all single diagonal entries (MaxCut-type: A_k = a_k e_d e_d^T).
+ * There A(sym(U V^T))_k = a_k <U_d, V_d> needs no off-diagonal sample, <C, U V^T> = <U, C V>, and
+ * (C + A^*(w)) X = C X + Diag(sum_k w_k a_k) X, so one ALM inner iteration is ONE sparse product T = C D
+ * plus row-local streaming work.  Row -> constraints is a CSR (rcptr, rcgid, rca) so several (or no)
+ * constraints per row are handled; MaxCut has exactly one.
+ * ================================================================================================*/
+
+/* T = C X over the full symmetric CSR with C's values stored per CSR entry.
+ * EPI: also q1_k = 2 a_k <R_i, X_i>, q2_k = a_k <X_i, X_i> for the constraints k of row i and the two
+ * objective terms sum_i <R_i, T_i> (p1/2) and sum_i <X_i, T_i> (p2)
+ *     reference: ALMCalq12p12 -> LORADSObjConstrValAll -> LORADSUVt/objAUV/coneAUV, lorads_alm.c:714-734,
+ *     lorads_alg_common.c:43-90,153-176 ; mul_rk, lorads_sdp_data.c:750-763 */
+template <int G, bool EPI>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
+                                                      const int32_t *__restrict__ fcol, const double *__restrict__ fval,
+                                                      const double *__restrict__ X, int ld, double *__restrict__ T,
+                                                      const double *__restrict__ Rm, const int32_t *__restrict__ rcptr,
+                                                      const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
+                                                      double *__restrict__ q1, double *__restrict__ q2, double *partials,
+                                                      unsigned int *counter, double *dsc, SlotSpec<2> spec)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (n + groups - 1) / groups;
+    double red[2] = {0.0, 0.0};
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        double rd = 0.0, dd = 0.0;
+        if (live) {
+            const int e0 = fptr[i], e1 = fptr[i + 1];
+            for (int cb = 0; cb < ld2; cb += G) {
+                const int c = cb + lane;
+                if (c < ld2) {
+                    double2 acc = make_double2(0.0, 0.0);
+                    int e = e0;
+                    for (; e + 3 < e1; e += 4) {
+                        const int c0 = fcol[e], c1 = fcol[e + 1], c2 = fcol[e + 2], c3 = fcol[e + 3];
+                        const double s0 = fval[e], s1 = fval[e + 1], s2 = fval[e + 2], s3 = fval[e + 3];
+                        const double2 x0 = reinterpret_cast<const double2 *>(X + (size_t)c0 * ld)[c];
+                        const double2 x1 = reinterpret_cast<const double2 *>(X + (size_t)c1 * ld)[c];
+                        const double2 x2 = reinterpret_cast<const double2 *>(X + (size_t)c2 * ld)[c];
+                        const double2 x3 = reinterpret_cast<const double2 *>(X + (size_t)c3 * ld)[c];
+                        acc.x = fma(s0, x0.x, acc.x); acc.y = fma(s0, x0.y, acc.y);
+                        acc.x = fma(s1, x1.x, acc.x); acc.y = fma(s1, x1.y, acc.y);
+                        acc.x = fma(s2, x2.x, acc.x); acc.y = fma(s2, x2.y, acc.y);
+                        acc.x = fma(s3, x3.x, acc.x); acc.y = fma(s3, x3.y, acc.y);
+                    }
+                    for (; e < e1; ++e) {
+                        const double s0 = fval[e];
+                        const double2 x0 = reinterpret_cast<const double2 *>(X + (size_t)fcol[e] * ld)[c];
+                        acc.x = fma(s0, x0.x, acc.x); acc.y = fma(s0, x0.y, acc.y);
+                    }
+                    reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
+                    if (EPI) {
+                        const double2 r = reinterpret_cast<const double2 *>(Rm + (size_t)i * ld)[c];
+                        const double2 d = reinterpret_cast<const double2 *>(X + (size_t)i * ld)[c];
+                        rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
+                        dd = fma(d.x, d.x, dd); dd = fma(d.y, d.y, dd);
+                        red[0] = fma(r.x, acc.x, red[0]); red[0] = fma(r.y, acc.y, red[0]);
+                        red[1] = fma(d.x, acc.x, red[1]); red[1] = fma(d.y, acc.y, red[1]);
+                    }
+                }
+            }
+        }
+        if (EPI) {
+            rd = group_sum<G>(rd);
+            dd = group_sum<G>(dd);
+            if (live && lane == 0)
+                for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) {
+                    const double a = rca[t];
+                    q1[rcgid[t]] = 2.0 * (a * rd);
+                    q2[rcgid[t]] = a * dd;
+                }
+        }
+    }
+    if (EPI) grid_reduce_finish<2>(red, partials, counter, dsc, spec);
+}
+
+/* One fused streaming pass for everything that follows the line search (tau known):
+ *   setAsNegGrad + ALMupdateVar + constrValSum += tau q1 + tau^2 q2      lorads_alm.c:1342-1353
+ *   ALMCalGrad: M1 = -lambda - rho b + rho constrValSum ; Grad = 2 (C R + Diag(A^*(M1)) R)   lorads_alm.c:32-87
+ *   setlbfgsHisTwo: s = tau D, y = Grad_new - Grad_old, <y,s>             lorads_alm.c:842-863
+ *   updateDimacsALM: constrValSum <- A(R R^T) from scratch, |b - A|^2      lorads_alg_common.c:386-394,424-428
+ * C R is carried as CR <- CR + tau (C D) with C D = T from k_mc_spmm.
+ * reductions: [0] sum Grad^2, [1] <y,s>, [2] sum (b - A(RR^T))^2 */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double tau, double rho, double *__restrict__ Rm,
+                                                      const double *__restrict__ D, double *__restrict__ CR,
+                                                      const double *__restrict__ T, double *__restrict__ Gd,
+                                                      double *__restrict__ sh, double *__restrict__ yh,
+                                                      const int32_t *__restrict__ rcptr, const int32_t *__restrict__ rcgid,
+                                                      const double *__restrict__ rca, const double *__restrict__ lam,
+                                                      const double *__restrict__ b, double *__restrict__ cvs,
+                                                      const double *__restrict__ q1, const double *__restrict__ q2,
+                                                      double *__restrict__ M1, double *partials, unsigned int *counter,
+                                                      double *dsc, SlotSpec<3> spec)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (n + groups - 1) / groups;
+    const double t2 = tau * tau;
+    double red[3] = {0.0, 0.0, 0.0};
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        double rr = 0.0;
+        int k0 = 0, k1 = 0;
+        if (live) {
+            k0 = rcptr[i];
+            k1 = rcptr[i + 1];
+            double coef = 0.0;
+            for (int t = k0; t < k1; ++t) {
+                const int k = rcgid[t];
+                const double cv = fma(t2, q2[k], fma(tau, q1[k], cvs[k]));
+                const double m1 = -lam[k] - rho * b[k] + rho * cv;
+                if (lane == 0) M1[k] = m1;
+                coef = fma(m1, rca[t], coef);
+            }
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                double2 r = reinterpret_cast<double2 *>(Rm)[w];
+                const double2 d = reinterpret_cast<const double2 *>(D)[w];
+                double2 cr = reinterpret_cast<double2 *>(CR)[w];
+                const double2 t = reinterpret_cast<const double2 *>(T)[w];
+                const double2 go = reinterpret_cast<double2 *>(Gd)[w];
+                r.x = fma(tau, d.x, r.x); r.y = fma(tau, d.y, r.y);
+                cr.x = fma(tau, t.x, cr.x); cr.y = fma(tau, t.y, cr.y);
+                double2 gn;
+                gn.x = 2.0 * fma(coef, r.x, cr.x);
+                gn.y = 2.0 * fma(coef, r.y, cr.y);
+                const double2 sv = make_double2(tau * d.x, tau * d.y);
+                const double2 yv = make_double2(-go.x + gn.x, -go.y + gn.y);
+                reinterpret_cast<double2 *>(Rm)[w] = r;
+                reinterpret_cast<double2 *>(CR)[w] = cr;
+                reinterpret_cast<double2 *>(Gd)[w] = gn;
+                reinterpret_cast<double2 *>(sh)[w] = sv;
+                reinterpret_cast<double2 *>(yh)[w] = yv;
+                red[0] = fma(gn.x, gn.x, red[0]); red[0] = fma(gn.y, gn.y, red[0]);
+                red[1] = fma(yv.x, sv.x, red[1]); red[1] = fma(yv.y, sv.y, red[1]);
+                rr = fma(r.x, r.x, rr); rr = fma(r.y, r.y, rr);
+            }
+        }
+        rr = group_sum<G>(rr);
+        if (live && lane == 0)
+            for (int t = k0; t < k1; ++t) {
+                const int k = rcgid[t];
+                const double cv = rca[t] * rr;
+                cvs[k] = cv;
+                const double df = b[k] - cv;
+                red[2] = fma(df, df, red[2]);
+            }
+    }
+    grid_reduce_finish<3>(red, partials, counter, dsc, spec);
+}
+
+/* Grad = 2 (CR + Diag(sum_k M1_k a_k) R) and sum Grad^2, with CR = C R already formed    lorads_alm.c:32-87 */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_grad(int64_t n, int ld, const double *__restrict__ Rm,
+                                                      const double *__restrict__ CR, double *__restrict__ Gd,
+                                                      const int32_t *__restrict__ rcptr, const int32_t *__restrict__ rcgid,
+                                                      const double *__restrict__ rca, const double *__restrict__ M1,
+                                                      double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    double red[1] = {0.0};
+    for (int64_t i = g0; i < n; i += groups) {
+        double coef = 0.0;
+        for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) coef = fma(M1[rcgid[t]], rca[t], coef);
+        for (int c = lane; c < ld2; c += G) {
+            const size_t w = (size_t)i * ld2 + c;
+            const double2 r = reinterpret_cast<const double2 *>(Rm)[w];
+            const double2 cr = reinterpret_cast<const double2 *>(CR)[w];
+            double2 gn;
+            gn.x = 2.0 * fma(coef, r.x, cr.x);
+            gn.y = 2.0 * fma(coef, r.y, cr.y);
+            reinterpret_cast<double2 *>(Gd)[w] = gn;
+            red[0] = fma(gn.x, gn.x, red[0]); red[0] = fma(gn.y, gn.y, red[0]);
+        }
+    }
+    grid_reduce_finish<1>(red, partials, counter, dsc, spec);
+}
+
+/* cvs_k = a_k <A_i, B_i> for the constraints k of row i (A(sym(A B^T)) for diagonal constraints); optional
+ * sum (b - cvs)^2          reference: LORADSInitConstrValAll/Sum + primalInfeasibility, lorads_alg_common.c:116-122,221-229,386-394 */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_rowdot(int64_t n, int ld, const double *__restrict__ A,
+                                                        const double *__restrict__ B, const int32_t *__restrict__ rcptr,
+                                                        const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
+                                                        double scale, double *__restrict__ out, const double *__restrict__ b,
+                                                        double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (n + groups - 1) / groups;
+    double red[1] = {0.0};
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        double ab = 0.0;
+        if (live)
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                const double2 x = reinterpret_cast<const double2 *>(A)[w];
+                const double2 y = reinterpret_cast<const double2 *>(B)[w];
+                ab = fma(x.x, y.x, ab); ab = fma(x.y, y.y, ab);
+            }
+        ab = group_sum<G>(ab);
+        if (live && lane == 0)
+            for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) {
+                const int k = rcgid[t];
+                const double cv = scale * (rca[t] * ab);
+                out[k] = cv;
+                if (b != nullptr) {
+                    const double df = b[k] - cv;
+                    red[0] = fma(df, df, red[0]);
+                }
+            }
+    }
+    if (b != nullptr) grid_reduce_finish<1>(red, partials, counter, dsc, spec);
+}
+
+/* CG operator for diagonal constraints: out = x + Diag(c_i <x_i, V_i>) V with c_i = sum_k a_k^2, and <p, out>
+ *     reference: linSysProduct / LORADSUpdateConstrValCG, lorads_admm.c:442-486 */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_cg_mvec(int64_t n, int ld, const double *__restrict__ X,
+                                                         const double *__restrict__ Vf, const int32_t *__restrict__ rcptr,
+                                                         const double *__restrict__ rca, double *__restrict__ out)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (n + groups - 1) / groups;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        double xv = 0.0;
+        if (live)
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                const double2 x = reinterpret_cast<const double2 *>(X)[w];
+                const double2 v = reinterpret_cast<const double2 *>(Vf)[w];
+                xv = fma(x.x, v.x, xv); xv = fma(x.y, v.y, xv);
+            }
+        xv = group_sum<G>(xv);
+        if (live) {
+            /* weight_k = a_k <x_i, V_i> ; the aggregate's diagonal entry is sum_k weight_k a_k (constraint order) */
+            double dg = 0.0;
+            for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) dg = fma(rca[t] * xv, rca[t], dg);
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                const double2 x = reinterpret_cast<const double2 *>(X)[w];
+                const double2 v = reinterpret_cast<const double2 *>(Vf)[w];
+                reinterpret_cast<double2 *>(out)[w] = make_double2(fma(dg, v.x, x.x), fma(dg, v.y, x.y));
+            }
+        }
+    }
+}
+
 #endif

@@ -76,6 +76,13 @@ def lib() -> ctypes.CDLL:
         "lgpu_last_error": (ctypes.c_char_p, [_vp]),
         "lgpu_version": (ctypes.c_char_p, []),
         "lgpu_launch_count": (i64, [_vp]),
+        "lgpu_sync": (i, [_vp]),
+        "lgpu_timer_record": (i, [_vp, i]),
+        "lgpu_timer_elapsed_ms": (i, [_vp, i, i, _c_dp]),
+        "lgpu_profile_enable": (i, [_vp, i]),
+        "lgpu_profile_read": (i, [_vp, i, _c_dp, _c_lp]),
+        "lgpu_profile_num_classes": (i, []),
+        "lgpu_profile_class_name": (ctypes.c_char_p, [i]),
         "lgpu_set_problem": (i, [_vp, i64, _c_dp, i, _c_lp, i64]),
         "lgpu_cone_upload": (i, [_vp, i, _c_lp, _c_lp, _c_dp]),
         "lgpu_lp_upload": (i, [_vp, _c_lp, _c_lp, _c_dp]),
@@ -98,6 +105,9 @@ def lib() -> ctypes.CDLL:
         "lgpu_lbfgs_direction": (i, [_vp, i64]),
         "lgpu_alm_linesearch_terms": (i, [_vp, d, _c_dp]),
         "lgpu_alm_step": (i, [_vp, d]),
+        "lgpu_alm_inner_update": (i, [_vp, d, d, _c_dp, _c_dp]),
+        "lgpu_set_fused_path": (i, [_vp, i]),
+        "lgpu_uses_fused_path": (i, [_vp]),
         "lgpu_lbfgs_push": (i, [_vp, d]),
         "lgpu_primal_infeasibility": (i, [_vp, i, _c_dp]),
         "lgpu_update_dual_var": (i, [_vp, d]),
@@ -287,6 +297,27 @@ class Context:
     def launch_count(self) -> int:
         return int(self._L.lgpu_launch_count(self._h))
 
+    # ---- timing hooks ---------------------------------------------------------------------------
+    def sync(self):
+        self._ck(self._L.lgpu_sync(self._h), "lgpu_sync")
+
+    def timer_record(self, slot: int):
+        self._ck(self._L.lgpu_timer_record(self._h, slot), "lgpu_timer_record")
+
+    def timer_elapsed_ms(self, a: int, b: int) -> float:
+        o = ctypes.c_double()
+        self._ck(self._L.lgpu_timer_elapsed_ms(self._h, a, b, ctypes.cast(ctypes.byref(o), _c_dp)), "lgpu_timer_elapsed_ms")
+        return o.value
+
+    def profile_enable(self, on: bool):
+        self._ck(self._L.lgpu_profile_enable(self._h, 1 if on else 0), "lgpu_profile_enable")
+
+    def profile_read(self) -> dict:
+        k = self._L.lgpu_profile_num_classes()
+        ms, cnt = np.zeros(k), np.zeros(k, np.int64)
+        self._ck(self._L.lgpu_profile_read(self._h, k, _dp(ms), _i64(cnt)), "lgpu_profile_read")
+        return {self._L.lgpu_profile_class_name(j).decode(): (float(ms[j]), int(cnt[j])) for j in range(k)}
+
     # ---- variables ----------------------------------------------------------------------------
     def alloc_vars(self, rank: Sequence[int], lbfgs_len: int = 2):
         r = np.ascontiguousarray(rank, dtype=np.int64)
@@ -349,6 +380,20 @@ class Context:
 
     def alm_step(self, tau: float):
         self._ck(self._L.lgpu_alm_step(self._h, float(tau)), "lgpu_alm_step")
+
+    def alm_inner_update(self, rho: float, tau: float):
+        """everything of an ALM inner iteration after the line search; returns (sum |Grad|^2, pInf_l1)"""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        self._ck(self._L.lgpu_alm_inner_update(self._h, float(rho), float(tau), ctypes.cast(ctypes.byref(a), _c_dp),
+                                               ctypes.cast(ctypes.byref(b), _c_dp)), "lgpu_alm_inner_update")
+        return a.value, b.value
+
+    def set_fused_path(self, on: bool):
+        self._ck(self._L.lgpu_set_fused_path(self._h, 1 if on else 0), "lgpu_set_fused_path")
+
+    @property
+    def uses_fused_path(self) -> bool:
+        return bool(self._L.lgpu_uses_fused_path(self._h))
 
     def lbfgs_push(self, tau: float):
         self._ck(self._L.lgpu_lbfgs_push(self._h, float(tau)), "lgpu_lbfgs_push")

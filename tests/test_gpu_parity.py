@@ -97,14 +97,23 @@ def _load_vars(ctx, g, nc, nlp):
         ctx.set_lp(0, g["rLp0"]); ctx.set_lp(1, g["uLp0"]); ctx.set_lp(2, g["vLp0"])
 
 
+MAXCUT = ("G11", "maxcut_torus_8x10", "maxcut_torus_20x30")
+
+
+@pytest.mark.parametrize("mode", ["split_calls", "inner_update", "general_path"])
 @pytest.mark.parametrize("name", FIXTURES)
-def test_alm_admm_sequence_vs_reference(lb, name):
+def test_alm_admm_sequence_vs_reference(lb, name, mode):
     """The exact call sequence oracle/make_golden.py drove through the reference: gradient, five ALM inner
     iterations (lorads_alm.c:1302-1378), objective, oracle rank, dual update, ALM->ADMM, one ADMM sweep with CG,
     ADMM objective / infeasibility, rank augmentation."""
     g, p, ctx, q, cones = _problem(lb, name)
     nc, nlp = len(cones), q.nlp
+    if mode == "general_path":
+        if name not in MAXCUT:
+            pytest.skip("only MaxCut-type problems have a fused path to switch off")
+        ctx.set_fused_path(False)
     _load_vars(ctx, g, nc, nlp)
+    assert ctx.uses_fused_path == (name in MAXCUT and mode != "general_path")
     for c in range(nc):  # host <-> device layout round trip is exact
         assert np.array_equal(ctx.get_factor(0, c), g[f"R0_{c}"])
     rho = float(g["rho0"])
@@ -124,10 +133,13 @@ def test_alm_admm_sequence_vs_reference(lb, name):
             assert rel(ctx.get_vec(lb.VEC_ARD), g["q1_first"]) < KTOL
             assert rel(ctx.get_vec(lb.VEC_ADD), g["q2_first"]) < KTOL
         nroot, tau = _line_search(lb, rho, terms)
-        ctx.alm_step(tau)
-        lag = ctx.alm_cal_grad(rho)
-        ctx.lbfgs_push(tau)
-        pinf = ctx.primal_infeasibility(lb.PAIR_RR)
+        if mode == "inner_update":
+            lag, pinf = ctx.alm_inner_update(rho, tau)
+        else:
+            ctx.alm_step(tau)
+            lag = ctx.alm_cal_grad(rho)
+            ctx.lbfgs_push(tau)
+            pinf = ctx.primal_infeasibility(lb.PAIR_RR)
         got = np.array([nroot, tau, terms[0], terms[1], lag, pinf])
         # scalars after `it` iterations: rounding differences compound through the L-BFGS recursion
         assert np.all(np.abs(got - sc[it]) <= 1e-9 * np.maximum(np.abs(sc[it]), 1e-300)), (it, got, sc[it])
@@ -153,6 +165,16 @@ def test_alm_admm_sequence_vs_reference(lb, name):
     assert rel(ctx.get_vec(lb.VEC_DUAL), g["lam1"]) < 1e-9
     ctx.alm_to_admm()
     ctx.init_constr_val(lb.PAIR_UV)
+    if nlp:
+        # LORADSADMMOptimize initialises with the NON-LP variants (lorads_admm.c:98-99), so constrValSum starts
+        # without the LP block's share (in a real solve updateDimacsADMM repairs it one line later); the golden
+        # sweep was recorded right after that initialisation, so reproduce it here
+        u, v = ctx.get_lp(lb.U), ctx.get_lp(lb.V)
+        share = np.zeros(p.m)
+        for i in range(p.m):
+            e = slice(p.lp_beg[i + 1], p.lp_beg[i + 2])
+            share[i] = np.sum(p.lp_elem[e] * u[p.lp_idx[e]] * v[p.lp_idx[e]])
+        ctx.set_vec(lb.VEC_CONSTR_SUM, ctx.get_vec(lb.VEC_CONSTR_SUM) - share)
     cgit = ctx.admm_update_var(float(g["rho_admm"]), float(g["cg_tol"]), 800, 0)
     ref_it = int(g["cg_iter"])
     assert abs(cgit - ref_it) <= max(2, 0.05 * ref_it), (cgit, ref_it)
@@ -234,6 +256,54 @@ def test_adjoint_and_linearity_at_scale(lb, shape):
     Y2 = ctx.op_wsum_mulrk(0, wv, Vm + Wm, True)
     assert rel(Y2, Y0 + Y1 + ctx.op_wsum_mulrk(0, wv, Wm, True)) < 1e-11
     ctx.close()
+
+
+def test_fused_path_tracks_general_path_at_c3_scale(lb):
+    """A/B at the G81-like size (n = 20000, rank 20): 40 ALM inner iterations + dual update + 1 ADMM sweep on the
+    fused MaxCut-type path and on the general path from the same start; trajectories must agree far inside the
+    solver's own tolerances (the carried C R and the regrouped sums only move rounding)."""
+    n, r = 20000, 20
+    ei, ej, w = lb.torus_graph(100, 200, 81)
+    p = lb.maxcut_problem(n, ei, ej, w)
+    rng = np.random.default_rng(925)
+    R0 = rng.random((n, r)) - rng.random((n, r))
+    rho = 1.0 / np.sqrt(n)
+    res = {}
+    for fused in (True, False):
+        ctx = lb.Context(0).load(p)
+        ctx.set_fused_path(fused)
+        ctx.alloc_vars([r], 2)
+        assert ctx.uses_fused_path == fused
+        ctx.set_factor(lb.R, 0, R0)
+        ctx.init_constr_val(lb.PAIR_RR)
+        ctx.alm_cal_grad(rho)
+        taus = []
+        for it in range(40):
+            ctx.lbfgs_direction(it)
+            terms = ctx.alm_linesearch_terms(rho)
+            _, tau = _line_search(lb, rho, terms)
+            lag, pinf = ctx.alm_inner_update(rho, tau)
+            taus.append((tau, lag, pinf, terms[0], terms[1]))
+        obj = ctx.cal_obj(False)
+        ctx.update_dual_var(rho)
+        lag2 = ctx.alm_cal_grad(rho)
+        Rf = ctx.get_factor(lb.R, 0)
+        Gf = ctx.get_factor(lb.GRAD, 0)
+        ctx.alm_to_admm()
+        ctx.init_constr_val(lb.PAIR_UV)
+        cg = ctx.admm_update_var(10 * rho, 1e-8, 800, 0)
+        Uf = ctx.get_factor(lb.U, 0)
+        objA = ctx.cal_obj(True)
+        launches = ctx.launch_count
+        res[fused] = (np.array(taus), obj, lag2, Rf, Gf, cg, Uf, objA, launches)
+        ctx.close()
+    a, b = res[True], res[False]
+    assert np.all(np.abs(a[0] - b[0]) <= 1e-8 * np.maximum(np.abs(b[0]), 1e-30)), np.max(np.abs(a[0] - b[0]) / np.abs(b[0]))
+    assert abs(a[1] - b[1]) <= 1e-10 * abs(b[1]) and abs(a[2] - b[2]) <= 1e-8 * abs(b[2])
+    assert rel(a[3], b[3]) < 1e-9 and rel(a[4], b[4]) < 1e-8
+    assert abs(a[5] - b[5]) <= max(2, 0.05 * b[5])
+    assert rel(a[6], b[6]) < 1e-6 and abs(a[7] - b[7]) <= 1e-8 * abs(b[7])
+    assert a[8] < b[8]  # and it is the cheaper path
 
 
 # ---- end to end: the drop-in binary next to the reference binary -----------------------------------------
