@@ -81,7 +81,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        """keep only the samples taken inside the timed region [t0, t1] (perf_counter stamps)"""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -93,7 +97,11 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", -1e300), getattr(self, "t1", 1e300)
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.15]
+        if not inside:  # region shorter than the sampling period: take the nearest samples around it
+            inside = [r for (t, r) in self.rows if t0 - 0.3 <= t <= t1 + 0.3]
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 for k, nm in enumerate(names):
@@ -261,19 +269,21 @@ def run_ours(args):
         ctx.alm_cal_grad(rho)
 
     # ---- device-resident timing -------------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
     start(True)
     k = 0
     for _ in range(args.warmup):
         alm_iteration(ctx, lb, H, rho, k); k += 1
     ctx.sync()
-    clocks = ClockSampler(local)
-    clocks.start()
     l0 = ctx.launch_count
+    tw0 = time.perf_counter()
     ctx.timer_record(0)
     for _ in range(args.steps):
         out = alm_iteration(ctx, lb, H, rho, k); k += 1
     ctx.timer_record(1)
     ctx.sync()
+    clocks.window(tw0, time.perf_counter())
     ms = ctx.timer_elapsed_ms(0, 1)
     launches = ctx.launch_count - l0
     clk = clocks.stop()

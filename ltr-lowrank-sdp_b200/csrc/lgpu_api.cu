@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <unordered_map>
 
 #include "../../include/lorads_b200.h"
 #include "lgpu_kernels.cuh"
@@ -72,10 +73,24 @@ static void dev_free(T *&p)
 /* ------------------------------------------------------------------------------------------------
  * launch helpers
  * ------------------------------------------------------------------------------------------------*/
-static inline int grid_for(const lgpu_ctx *ctx, int64_t threads_needed)
+/* grid = min(blocks needed, SMs x resident CTAs of THIS kernel): every launch is at most one full wave, grid-stride
+ * loops cover the rest, so there is no partial last wave (148 SMs; occupancy queried once per kernel and cached) */
+static std::unordered_map<const void *, int> g_occ;
+static inline int grid_for(const lgpu_ctx *ctx, int64_t threads_needed, const void *kernel = nullptr)
 {
     int64_t blocks = (threads_needed + LGPU_TPB - 1) / LGPU_TPB;
-    int64_t cap = (int64_t)ctx->num_sms * 8;
+    int per_sm = 8;
+    if (kernel != nullptr) {
+        auto it = g_occ.find(kernel);
+        if (it == g_occ.end()) {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, LGPU_TPB, 0) != cudaSuccess || occ < 1) occ = 4;
+            if (occ > 8) occ = 8;
+            it = g_occ.emplace(kernel, occ).first;
+        }
+        per_sm = it->second;
+    }
+    int64_t cap = (int64_t)ctx->num_sms * per_sm;
     if (cap > LGPU_MAX_PARTIAL_BLOCKS) cap = LGPU_MAX_PARTIAL_BLOCKS;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -123,13 +138,19 @@ static void launch_map(lgpu_ctx *ctx, int64_t n, F f)
 {
     if (n <= 0) return;
     Prof pr(ctx, KC_VEC);
-    k_map<<<grid_for(ctx, n), LGPU_TPB, 0, ctx->stream>>>(n, f);
+    k_map<<<grid_for(ctx, n, (const void *)k_map<F>), LGPU_TPB, 0, ctx->stream>>>(n, f);
+}
+template <int K, class F, class P>
+static void launch_reduce_post(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec, P post, int cls = KC_REDUCE)
+{
+    Prof pr(ctx, cls);
+    k_reduce<K, F, P><<<grid_for(ctx, n > 0 ? n : 1, (const void *)k_reduce<K, F, P>), LGPU_TPB, 0, ctx->stream>>>(
+        n, f, ctx->partials, ctx->counter, ctx->dsc, spec, post);
 }
 template <int K, class F>
 static void launch_reduce(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec)
 {
-    Prof pr(ctx, KC_REDUCE);
-    k_reduce<K><<<grid_for(ctx, n > 0 ? n : 1), LGPU_TPB, 0, ctx->stream>>>(n, f, ctx->partials, ctx->counter, ctx->dsc, spec);
+    launch_reduce_post<K>(ctx, n, f, spec, NoPost());
 }
 template <class F>
 static void launch_scalar(lgpu_ctx *ctx, F f)
@@ -183,7 +204,7 @@ static void run_uvt(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *U, cons
     const int G = pick_group(ld);
     const int same = (U == V) ? 1 : 0;
     Prof pr(ctx, KC_UVT);
-    DISPATCH_G(G, k_uvt<GG><<<grid_for(ctx, c.nnzP * GG), LGPU_TPB, 0, ctx->stream>>>(
+    DISPATCH_G(G, k_uvt<GG><<<grid_for(ctx, c.nnzP * GG, (const void *)k_uvt<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.nnzP, c.pat_row, c.pat_col, U, V, (int)ld, same, out));
 }
 /* cv = A_c(uvt) (compact, per non-zero constraint) */
@@ -218,7 +239,7 @@ static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, con
 {
     const int G = pick_group(ld);
     Prof pr(ctx, KC_SPMM);
-    DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+    DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG, (const void *)k_spmm<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, c.f_ptr, c.f_col, c.f_slot, S, X, (int)ld, alpha, beta, Z, Y));
 }
 
@@ -1072,7 +1093,7 @@ static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double sc
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
     Prof pr(ctx, KC_GATHER);
-    DISPATCH_G(G, k_mc_rowdot<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+    DISPATCH_G(G, k_mc_rowdot<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_rowdot<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, (int)c.ld, A, B, c.rc_ptr, c.rc_gid, c.rc_a, scale, out, with_pinf ? ctx->b : nullptr,
                       ctx->partials, ctx->counter, ctx->dsc, slot1(SC_PINF, 0)));
 }
@@ -1084,7 +1105,7 @@ static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
     SlotSpec<2> sp;
     sp.slot[0] = SC_TMP; sp.slot[1] = SC_TMP2; sp.accumulate = 0;
     Prof pr(ctx, KC_MC_SPMM);
-    DISPATCH_G(G, k_mc_spmm<GG, false><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+    DISPATCH_G(G, k_mc_spmm<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, c.f_ptr, c.f_col, c.mc_val, X, (int)c.ld, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                       ctx->partials, ctx->counter, ctx->dsc, sp));
 }
@@ -1101,7 +1122,7 @@ static void mc_grad(lgpu_ctx *ctx)
     if (!ctx->cr_valid) mc_refresh_cr(ctx);
     const int G = pick_group(c.ld);
     Prof pr(ctx, KC_MC_STEP);
-    DISPATCH_G(G, k_mc_grad<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+    DISPATCH_G(G, k_mc_grad<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_grad<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, (int)c.ld, ctx->R, ctx->CR, ctx->G, c.rc_ptr, c.rc_gid, c.rc_a, ctx->M1, ctx->partials, ctx->counter,
                       ctx->dsc, slot1(SC_LAG, 0)));
 }
@@ -1223,35 +1244,63 @@ extern "C" int lgpu_lbfgs_direction(lgpu_ctx *ctx, int64_t inner_iter)
     }
     const int h = ctx->h;
     const int nn = (int)((inner_iter <= (ctx->lp.n > 0 ? h : h - 1)) ? inner_iter : h); /* Q4: LP variant uses <= h */
-    /* two-loop recursion (lorads_alm.c:468-505), q lives in D */
-    CU(ctx, cudaMemcpyAsync(D, G, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
-    int node = (ctx->head - 1 + h) % h;
-    for (int k = 0; k < nn; ++k) {
-        const double *s = ctx->s[node], *y = ctx->y[node];
-        launch_reduce<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(s[i], D[i], acc[0]); }, slot1(SC_TMP));
-        const int ia = SC_ALPHA0 + node, ib = SC_BETA0 + node;
-        launch_scalar(ctx, [=] __device__() { dsc[ia] = dsc[ib] * dsc[SC_TMP]; });
-        launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = fma(-dsc[ia], y[i], D[i]); });
-        node = (node - 1 + h) % h;
+    /* two-loop recursion (lorads_alm.c:468-505) as 2 nn + 1 fused passes: every pass applies the previous axpy and
+     * accumulates the next dot product; the derived scalar (alpha or alpha - beta <y,q>) is formed by the pass's
+     * finishing thread.  Same operations in the same order as the plain recursion. */
+    int j[16];
+    j[0] = (ctx->head - 1 + h) % h;
+    for (int k = 1; k < nn; ++k) j[k] = (j[k - 1] - 1 + h) % h;
+    {
+        const double *s0 = ctx->s[j[0]];
+        const int ia = SC_ALPHA0 + j[0], ib = SC_BETA0 + j[0];
+        launch_reduce_post<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(s0[i], G[i], acc[0]); },
+                              slot1(SC_TMP), [=] __device__(double *sc) { sc[ia] = sc[ib] * sc[SC_TMP]; }, KC_MC_DIR);
     }
-    node = (node + 1) % h;
     for (int k = 0; k < nn; ++k) {
-        const double *s = ctx->s[node], *y = ctx->y[node];
-        launch_reduce<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(y[i], D[i], acc[0]); }, slot1(SC_TMP));
-        const int ia = SC_ALPHA0 + node, ib = SC_BETA0 + node;
-        launch_scalar(ctx, [=] __device__() { dsc[SC_TMP2] = dsc[ia] - dsc[ib] * dsc[SC_TMP]; });
-        launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = fma(dsc[SC_TMP2], s[i], D[i]); });
-        node = (node + 1) % h;
+        const double *src = (k == 0) ? G : D;
+        const double *yk = ctx->y[j[k]];
+        const int ia = SC_ALPHA0 + j[k];
+        if (k < nn - 1) {
+            const double *dv = ctx->s[j[k + 1]];
+            const int ia2 = SC_ALPHA0 + j[k + 1], ib2 = SC_BETA0 + j[k + 1];
+            launch_reduce_post<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double v = fma(-dsc[ia], yk[i], src[i]);
+                D[i] = v;
+                acc[0] = fma(dv[i], v, acc[0]);
+            }, slot1(SC_TMP), [=] __device__(double *sc) { sc[ia2] = sc[ib2] * sc[SC_TMP]; }, KC_MC_DIR);
+        } else {
+            const int ib = SC_BETA0 + j[k];
+            launch_reduce_post<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double v = fma(-dsc[ia], yk[i], src[i]);
+                D[i] = v;
+                acc[0] = fma(yk[i], v, acc[0]);
+            }, slot1(SC_TMP), [=] __device__(double *sc) { sc[SC_TMP2] = sc[ia] - sc[ib] * sc[SC_TMP]; }, KC_MC_DIR);
+        }
     }
-    /* D = -q and <D, Grad> in one pass; then LBFGSDirectionUseGrad (lorads_alm.c:607-627) */
-    launch_reduce<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) {
-        const double d = -D[i];
-        D[i] = d;
-        acc[0] = fma(d, G[i], acc[0]);
-    }, slot1(SC_DG));
-    launch_map(ctx, N, [=] __device__(int64_t i) {
-        if (dsc[SC_DG] >= 0.0) D[i] = -G[i];
-    });
+    for (int k = nn - 1; k >= 0; --k) {
+        const double *sk = ctx->s[j[k]];
+        if (k > 0) {
+            const double *dv = ctx->y[j[k - 1]];
+            const int ia2 = SC_ALPHA0 + j[k - 1], ib2 = SC_BETA0 + j[k - 1];
+            launch_reduce_post<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double v = fma(dsc[SC_TMP2], sk[i], D[i]);
+                D[i] = v;
+                acc[0] = fma(dv[i], v, acc[0]);
+            }, slot1(SC_TMP), [=] __device__(double *sc) { sc[SC_TMP2] = sc[ia2] - sc[ib2] * sc[SC_TMP]; }, KC_MC_DIR);
+        } else {
+            /* last axpy, D = -q and <D, Grad> in one pass */
+            launch_reduce_post<1>(ctx, N, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double v = -fma(dsc[SC_TMP2], sk[i], D[i]);
+                D[i] = v;
+                acc[0] = fma(v, G[i], acc[0]);
+            }, slot1(SC_DG), NoPost(), KC_MC_DIR);
+        }
+    }
+    /* LBFGSDirectionUseGrad (lorads_alm.c:607-627) */
+    {
+        Prof pr(ctx, KC_VEC);
+        k_neg_if_nonneg<<<grid_for(ctx, N, (const void *)k_neg_if_nonneg), LGPU_TPB, 0, ctx->stream>>>(N, dsc, SC_DG, G, D);
+    }
     CHECK_LAUNCH(ctx);
     return 0;
 }
@@ -1269,7 +1318,7 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
         sp.slot[0] = SC_P1; sp.slot[1] = SC_P2; sp.accumulate = 0;
         {
             Prof pr(ctx, KC_MC_SPMM);
-            DISPATCH_G(G, k_mc_spmm<GG, true><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+            DISPATCH_G(G, k_mc_spmm<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
                               c.n, c.f_ptr, c.f_col, c.mc_val, ctx->U, (int)c.ld, ctx->CD, ctx->R, c.rc_ptr, c.rc_gid, c.rc_a,
                               ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, sp));
         }
@@ -1387,14 +1436,11 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
     sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
     {
         Prof pr(ctx, KC_MC_STEP);
-        DISPATCH_G(G, k_mc_step<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(
+        DISPATCH_G(G, k_mc_step<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[ctx->head], ctx->y[ctx->head],
                           c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->partials,
-                          ctx->counter, ctx->dsc, sp));
+                          ctx->counter, ctx->dsc, sp, SC_BETA0 + ctx->head));
     }
-    double *dsc = ctx->dsc;
-    const int ib = SC_BETA0 + ctx->head;
-    launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
     ctx->head = (ctx->head + 1) % ctx->h;
     ctx->cr_updates++;
     if (ctx->cr_updates >= 64) mc_refresh_cr(ctx); /* bound the rounding drift of the carried C R */
@@ -1524,7 +1570,7 @@ static void cg_mvec(lgpu_ctx *ctx, DevCone &c, const double *x, const double *fi
         /* diagonal constraints: the whole operator is row-local, x_i + (sum_k a_k^2) <x_i, V_i> V_i */
         const int G = pick_group(c.ld);
         Prof pr(ctx, KC_MC_STEP);
-        DISPATCH_G(G, k_mc_cg_mvec<GG><<<grid_for(ctx, c.n * GG), LGPU_TPB, 0, ctx->stream>>>(c.n, (int)c.ld, x, fixed, c.rc_ptr,
+        DISPATCH_G(G, k_mc_cg_mvec<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_cg_mvec<GG>), LGPU_TPB, 0, ctx->stream>>>(c.n, (int)c.ld, x, fixed, c.rc_ptr,
                                                                                              c.rc_a, res));
         return;
     }

@@ -40,9 +40,15 @@ struct SlotSpec {
 
 /* Deterministic grid reduction tail: block-sum K values, publish per-block partials, the LAST block
  * to arrive sums the partials in a fixed (thread-strided, then tree) order and writes dsc[slot]. */
-template <int K>
+struct NoPost {
+    __device__ void operator()(double *) const {}
+};
+
+/* `post(dsc)` runs once, in the finishing thread, after the slots are written: derived scalars (an L-BFGS alpha,
+ * 1/<y,s>, ...) are produced without a separate one-thread launch. */
+template <int K, class P = NoPost>
 __device__ __forceinline__ void grid_reduce_finish(double (&v)[K], double *partials, unsigned int *counter,
-                                                   double *dsc, const SlotSpec<K> &spec)
+                                                   double *dsc, const SlotSpec<K> &spec, P post = P())
 {
     __shared__ double sh[K][LGPU_TPB / 32];
     __shared__ bool is_last;
@@ -85,6 +91,7 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[K], double *parti
             if (spec.accumulate) dsc[spec.slot[k]] += t;
             else dsc[spec.slot[k]] = t;
         }
+        post(dsc);
         *counter = 0u;
     }
 }
@@ -97,16 +104,26 @@ __global__ void __launch_bounds__(LGPU_TPB) k_map(int64_t n, F f)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
 
-template <int K, class F>
+template <int K, class F, class P>
 __global__ void __launch_bounds__(LGPU_TPB) k_reduce(int64_t n, F f, double *partials, unsigned int *counter,
-                                                     double *dsc, SlotSpec<K> spec)
+                                                     double *dsc, SlotSpec<K> spec, P post)
 {
     double acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
-    grid_reduce_finish<K>(acc, partials, counter, dsc, spec);
+    grid_reduce_finish<K, P>(acc, partials, counter, dsc, spec, post);
+}
+
+/* D = -G where the device scalar dsc[slot] >= 0 (LBFGSDirectionUseGrad, lorads_alm.c:607-627); the test is made once
+ * per thread, so the common case (descent direction found) touches no memory */
+__global__ void __launch_bounds__(LGPU_TPB) k_neg_if_nonneg(int64_t n, const double *__restrict__ dsc, int slot,
+                                                            const double *__restrict__ G, double *__restrict__ D)
+{
+    if (!(dsc[slot] >= 0.0)) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) D[i] = -G[i];
 }
 
 template <class F>
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double 
                                                       const double *__restrict__ b, double *__restrict__ cvs,
                                                       const double *__restrict__ q1, const double *__restrict__ q2,
                                                       double *__restrict__ M1, double *partials, unsigned int *counter,
-                                                      double *dsc, SlotSpec<3> spec)
+                                                      double *dsc, SlotSpec<3> spec, int beta_slot)
 {
     const int lane = threadIdx.x % G;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -594,7 +611,9 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double 
                 red[2] = fma(df, df, red[2]);
             }
     }
-    grid_reduce_finish<3>(red, partials, counter, dsc, spec);
+    const int ys_slot = spec.slot[1];
+    grid_reduce_finish<3>(red, partials, counter, dsc, spec,
+                          [=] __device__(double *sc) { sc[beta_slot] = 1.0 / sc[ys_slot]; });
 }
 
 /* Grad = 2 (CR + Diag(sum_k M1_k a_k) R) and sum Grad^2, with CR = C R already formed    lorads_alm.c:32-87 */

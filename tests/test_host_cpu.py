@@ -149,4 +149,4 @@ def test_product_never_imports_oracle():
         for fn in files:
             if fn.endswith((".py", ".c", ".h", ".cu", ".cuh")) or fn == "Makefile":
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
-                assert "lorads_oracle" not in txt and "oracle/" not in txt and "_ref" not in txt, fn
+                assert "lorads_oracle" not in txt and "oracle/" not in txt and "lorads_ref" not in txt, fn
