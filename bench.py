@@ -134,17 +134,18 @@ def alm_iteration(ctx, lb, H, rho, k):
     return tau, lag, pinf
 
 
-def algorithmic_bytes(cls, info, n, ld, m, nlaunch_per_step):
+def algorithmic_bytes(cls, info, n, ld, m, share=1.0):
     """compulsory HBM bytes of ONE launch of a kernel class on this workload (every operand once, outputs once,
-    int32 indices) -- DESIGN.md 'Algorithmic bytes'."""
-    F = 8.0 * n * ld
-    nnzP, nnzF = info["nnzP"], 2 * info["nnzP"] - n
+    int32 indices) -- DESIGN.md 'Algorithmic bytes'.  `share` = fraction of the rows this rank owns."""
+    F = 8.0 * n * ld * share
+    nnzP, nnzF = info["nnzP"] * share, (2 * info["nnzP"] - n) * share
+    m = m * share
     if cls == "k_uvt":       # 3 launches / step: (R,D) reads two factors, (D,D) and (R,R) one
         return 16.0 * nnzP + F * (4.0 / 3.0)
     if cls == "k_spmm":
         return 8.0 * nnzF + 8.0 * nnzP + 4.0 * (n + 1) + 2 * F
-    if cls == "k_mc_spmm":
-        return 12.0 * nnzF + 4.0 * (n + 1) + 3 * F + 16.0 * m
+    if cls == "k_mc_spmm":   # CSR + own rows of R, D + T written; a partitioned rank also reads the other ranks' D rows once
+        return 12.0 * nnzF + 4.0 * (n * share + 1) + 3 * F + 16.0 * m + 8.0 * n * ld * (1.0 - share)
     if cls == "k_mc_step":
         return 10 * F + 56.0 * m
     if cls == "k_mc_dir":    # five fused passes: 13 F read + 4 F written over 5 launches
@@ -236,21 +237,32 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("row-block partitioned path: see bench_multi in DESIGN.md (not wired in this build)")
     torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        # torch.distributed is the plumbing (rendezvous, id broadcast, barrier, max over ranks); the data path's
+        # collectives are NCCL calls made by the library itself on its own communicator
+        import torch.distributed as dist
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl")
     H = lb.host_lib()
     n, r = args.n, args.rank
     t0 = time.perf_counter()
     p, nedges = build_problem(lb, n, args.out_degree, args.seed)
     t_gen = time.perf_counter() - t0
     ctx = lb.Context(local)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(lb.nccl_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.numpy().tobytes()), rank, world)
     t0 = time.perf_counter()
     ctx.load(p)
     t_upload = time.perf_counter() - t0
     info = ctx.cone_info(0)
     ctx.alloc_vars([r], 2)
     ld = (r + 3) // 4 * 4
+    n_loc = n if world == 1 else lb.partition_rows(n, world, rank)[2]
     # seeded host initial point in pinned memory (the reference's rand()/RAND_MAX - rand()/RAND_MAX distribution)
     rng = np.random.default_rng(925)
     R0 = torch.empty((r, n), dtype=torch.float64, pin_memory=True)   # column-major n x r
@@ -276,6 +288,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         alm_iteration(ctx, lb, H, rho, k); k += 1
     ctx.sync()
+    if dist is not None:
+        dist.barrier()
     l0 = ctx.launch_count
     tw0 = time.perf_counter()
     ctx.timer_record(0)
@@ -283,8 +297,14 @@ def run_ours(args):
         out = alm_iteration(ctx, lb, H, rho, k); k += 1
     ctx.timer_record(1)
     ctx.sync()
+    if dist is not None:
+        dist.barrier()
     clocks.window(tw0, time.perf_counter())
     ms = ctx.timer_elapsed_ms(0, 1)
+    if dist is not None:  # device time of the slowest rank
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
     launches = ctx.launch_count - l0
     clk = clocks.stop()
     value = args.steps / (ms * 1e-3)
@@ -299,7 +319,7 @@ def run_ours(args):
     dom = max(prof.items(), key=lambda kv: kv[1][0])
     peak, peak_src = peaks()
     per_launch_ms = dom[1][0] / max(dom[1][1], 1)
-    ab = algorithmic_bytes(dom[0], info, n, ld, n, dom[1][1] / args.steps)
+    ab = algorithmic_bytes(dom[0], info, n, ld, n, n_loc / n)
     roof = {"bound": "hbm", "kernel": dom[0], "share_of_step": dom[1][0] / tot, "launches_per_step": dom[1][1] / args.steps,
             "ms_per_launch": per_launch_ms, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
             "classes": {kname: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
@@ -314,6 +334,8 @@ def run_ours(args):
 
     # ---- end to end from host buffers ----------------------------------------------------------------------
     ctx.sync()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     start(True)
     for kk in range(args.steps):
@@ -323,6 +345,10 @@ def run_ours(args):
     cvs = ctx.get_vec(lb.VEC_CONSTR_SUM)
     ctx.sync()
     e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
     h2d = (8.0 * n * r + 8.0 * n) / args.steps
     d2h = (8.0 * n * r + 16.0 * n) / args.steps + 9 * 8
     assert np.isfinite(Rfin).all() and np.isfinite(out[2])
@@ -336,7 +362,11 @@ def run_ours(args):
             "gpu_launches": int(launches), "roofline": roof,
             "setup_s": {"generate": t_gen, "preprocess_upload": t_upload},
             "last_step": {"tau": out[0], "grad_norm_sq": out[1], "pinf": out[2]}}
-    if not args.no_cpu_baseline:
+    if rank != 0:
+        ctx.close()
+        dist.destroy_process_group()
+        return
+    if not args.no_cpu_baseline and world == 1:
         os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
         cb = reference_rate(args, args.cpu_sample_steps, 2)
         if cb is not None:
@@ -345,7 +375,9 @@ def run_ours(args):
                                               f"{cb['steps']} iterations in {cb['seconds']:.1f} s = {cb['sample_rate']:.3f} it/s, "
                                               f"scaled by n_sample/n"}
     ctx.close()
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -167,6 +167,18 @@ int lgpu_op_wsum(lgpu_ctx *ctx, int cone, const double *w, int add_obj, double *
 int lgpu_op_wsum_mulrk(lgpu_ctx *ctx, int cone, int64_t r, const double *w, int add_obj, const double *X,
                        double *Y);
 
+/* ---- multi-GPU: row-block partition over the GPUs of one node, one process per GPU -----------
+ * Rank p owns rows [lo, hi) of every factor-shaped array, the CSR rows of C and the constraints attached to those
+ * rows.  Exchange steps: one NCCL all-gather of the direction's rows before the sparse product, and NCCL all-reduces
+ * of the scalar packs (L-BFGS dots, the seven line-search terms, |Grad|^2 / <y,s> / |b - A|^2, CG dots).  This build
+ * partitions the fused MaxCut-type layout (one SDP block, single-diagonal-entry constraints).
+ * Order of calls: lgpu_create, lgpu_comm_init, lgpu_set_problem, lgpu_cone_upload (every rank passes the WHOLE
+ * problem and keeps its slice), lgpu_alloc_vars, ... ; host factors/vectors passed in or out are always whole. */
+int lgpu_partition_rows(int64_t n, int world, int rank, int64_t *lo, int64_t *hi, int64_t *rows_per_rank);
+/* ncclUniqueId is 128 bytes; rank 0 calls lgpu_nccl_unique_id and the host side distributes it to the other ranks */
+int lgpu_nccl_unique_id(unsigned char id[128]);
+int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int rank, int world);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <type_traits>
 #include <unordered_map>
 
 #include "../../include/lorads_b200.h"
@@ -140,9 +141,26 @@ static void launch_map(lgpu_ctx *ctx, int64_t n, F f)
     Prof pr(ctx, KC_VEC);
     k_map<<<grid_for(ctx, n, (const void *)k_map<F>), LGPU_TPB, 0, ctx->stream>>>(n, f);
 }
+template <int K> static int allreduce_spec(lgpu_ctx *ctx, const SlotSpec<K> &sp);
+template <class F> static void launch_scalar(lgpu_ctx *ctx, F f);
+/* fused elementwise + reduction pass.  One GPU: the finishing thread also forms the derived scalar (`post`).
+ * Partitioned: local sums, NCCL all-reduce of the slots in stream, then `post` as a one-thread kernel. */
 template <int K, class F, class P>
 static void launch_reduce_post(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec, P post, int cls = KC_REDUCE)
 {
+    if (ctx->world > 1) {
+        {
+            Prof pr(ctx, cls);
+            k_reduce<K, F, NoPost><<<grid_for(ctx, n > 0 ? n : 1, (const void *)k_reduce<K, F, NoPost>), LGPU_TPB, 0, ctx->stream>>>(
+                n, f, ctx->partials, ctx->counter, ctx->dsc, spec, NoPost());
+        }
+        if (allreduce_spec<K>(ctx, spec) != 0) return;
+        if (!std::is_same<P, NoPost>::value) {
+            double *dsc = ctx->dsc;
+            launch_scalar(ctx, [=] __device__() { post(dsc); });
+        }
+        return;
+    }
     Prof pr(ctx, cls);
     k_reduce<K, F, P><<<grid_for(ctx, n > 0 ? n : 1, (const void *)k_reduce<K, F, P>), LGPU_TPB, 0, ctx->stream>>>(
         n, f, ctx->partials, ctx->counter, ctx->dsc, spec, post);
@@ -174,6 +192,124 @@ static int fetch_scalars(lgpu_ctx *ctx, int first, int count)
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * NCCL (row-block partitioned runs).  The library is bound at run time so that single-GPU use has no NCCL
+ * dependency; only the few entry points used here are declared.
+ * ------------------------------------------------------------------------------------------------*/
+#include <dlfcn.h>
+typedef struct { char internal[128]; } lg_ncclUniqueId;
+typedef void *lg_ncclComm_t;
+enum { LG_NCCL_FLOAT64 = 8, LG_NCCL_SUM = 0 };
+static struct {
+    bool ready = false;
+    int (*GetUniqueId)(lg_ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(lg_ncclComm_t *, int, lg_ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(lg_ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, lg_ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, lg_ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+
+static bool nccl_load(std::string &err)
+{
+    if (g_nccl.ready) return true;
+    const char *cands[] = {getenv("LORADS_NCCL_LIB"), "libnccl.so.2",
+#ifdef LORADS_NCCL_PATH
+                           LORADS_NCCL_PATH,
+#endif
+                           "libnccl.so"};
+    void *h = nullptr;
+    for (const char *cnd : cands) {
+        if (!cnd) continue;
+        h = dlopen(cnd, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { err = "cannot load libnccl.so.2 (set LORADS_NCCL_LIB)"; return false; }
+    *(void **)&g_nccl.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+    *(void **)&g_nccl.CommInitRank = dlsym(h, "ncclCommInitRank");
+    *(void **)&g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void **)&g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
+    *(void **)&g_nccl.AllGather = dlsym(h, "ncclAllGather");
+    *(void **)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather) {
+        err = "libnccl lacks a required symbol";
+        return false;
+    }
+    g_nccl.ready = true;
+    return true;
+}
+#define NC(ctx, call)                                                                                   \
+    do {                                                                                                \
+        int _r = (call);                                                                                \
+        if (_r != 0) LGPU_FAIL(ctx, "%s:%d NCCL error %s: %s", __FILE__, __LINE__, #call,               \
+                               g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");                \
+    } while (0)
+
+/* sum dsc[first .. first+count) over the ranks, in stream (no-op on one GPU) */
+static int allreduce_scalars(lgpu_ctx *ctx, int first, int count)
+{
+    if (ctx->world <= 1) return 0;
+    NC(ctx, g_nccl.AllReduce(ctx->dsc + first, ctx->dsc + first, (size_t)count, LG_NCCL_FLOAT64, LG_NCCL_SUM,
+                             (lg_ncclComm_t)ctx->comm, ctx->stream));
+    return 0;
+}
+template <int K>
+static int allreduce_spec(lgpu_ctx *ctx, const SlotSpec<K> &sp)
+{
+    if (ctx->world <= 1) return 0;
+    int lo = sp.slot[0], hi = sp.slot[0];
+    for (int k = 1; k < K; ++k) { lo = std::min(lo, sp.slot[k]); hi = std::max(hi, sp.slot[k]); }
+    if (hi - lo + 1 == K) return allreduce_scalars(ctx, lo, K);
+    for (int k = 0; k < K; ++k) TRY(allreduce_scalars(ctx, sp.slot[k], 1));
+    return 0;
+}
+
+extern "C" int lgpu_partition_rows(int64_t n, int world, int rank, int64_t *lo, int64_t *hi, int64_t *rows_per_rank)
+{
+    if (n <= 0 || world <= 0 || rank < 0 || rank >= world) return 1;
+    const int64_t rpr = (n + world - 1) / world;
+    *rows_per_rank = rpr;
+    *lo = std::min<int64_t>((int64_t)rank * rpr, n);
+    *hi = std::min<int64_t>(*lo + rpr, n);
+    return 0;
+}
+extern "C" int lgpu_nccl_unique_id(unsigned char id[128])
+{
+    std::string err;
+    if (!nccl_load(err)) return 1;
+    lg_ncclUniqueId u;
+    if (g_nccl.GetUniqueId(&u) != 0) return 1;
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+extern "C" int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int rank, int world)
+{
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (world == 1) { ctx->rank = 0; ctx->world = 1; return 0; }
+    std::string err;
+    if (!nccl_load(err)) LGPU_FAIL(ctx, "%s", err.c_str());
+    lg_ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    lg_ncclComm_t comm = nullptr;
+    NC(ctx, g_nccl.CommInitRank(&comm, world, u, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    return 0;
+}
+
+/* constraints this rank owns: all of them on one GPU; in a partitioned run those attached to its rows.  m-vector
+ * kernels iterate t in [0, count) and touch entry k = gid ? gid[t] : t, so non-owned entries are never written. */
+struct Owned {
+    int64_t count;
+    const int32_t *gid;
+};
+static Owned owned(const lgpu_ctx *ctx)
+{
+    if (ctx->world > 1) return {ctx->cones[0].m_loc, ctx->cones[0].rc_gid};
+    return {ctx->m, nullptr};
+}
 static inline int pick_group(int64_t ld)
 {
     const int64_t words = ld / 2;
@@ -361,7 +497,7 @@ static void free_vars(lgpu_ctx *ctx)
 {
     dev_free(ctx->R); dev_free(ctx->U); dev_free(ctx->V); dev_free(ctx->G); dev_free(ctx->M2); dev_free(ctx->bLin);
     dev_free(ctx->cg_r); dev_free(ctx->cg_p); dev_free(ctx->cg_Q); dev_free(ctx->stage);
-    dev_free(ctx->CR); dev_free(ctx->CD);
+    dev_free(ctx->CR); dev_free(ctx->CD); dev_free(ctx->gfull);
     ctx->cr_valid = ctx->cd_valid = false;
     ctx->mc = false;
     for (auto &p : ctx->s) dev_free(p);
@@ -384,6 +520,7 @@ extern "C" void lgpu_destroy(lgpu_ctx *ctx)
     dev_free(ctx->lp.c_ptr); dev_free(ctx->lp.c_row); dev_free(ctx->lp.c_val); dev_free(ctx->lp.nrm2sq);
     dev_free(ctx->dsc); dev_free(ctx->partials); dev_free(ctx->counter);
     prof_flush(ctx);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((lg_ncclComm_t)ctx->comm);
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     for (auto &e : ctx->timers) if (e) cudaEventDestroy(e);
     if (ctx->hsc) cudaFreeHost(ctx->hsc);
@@ -651,6 +788,52 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     }
     /* upload */
     free_cone(c);
+    c.n_glob = n;
+    c.row_lo = 0;
+    c.n_alloc = n;
+    c.m_loc = mA;
+    if (ctx->world > 1) {
+        /* row-block partition: this rank keeps the CSR rows, the row -> constraint lists and the vector rows of
+         * [lo, hi); column indices and constraint ids stay global (they index the all-gathered factor and the
+         * replicated-length m-vectors).  Only the fused MaxCut-type layout is partitioned in this build. */
+        if (!(diag_only && mA == m && ctx->ncones == 1 && ctx->lp.n == 0))
+            LGPU_FAIL(ctx, "row-block partitioned runs need one SDP block with single-diagonal-entry constraints (MaxCut-type)");
+        int64_t lo, hi, rpr;
+        lgpu_partition_rows(n, ctx->world, ctx->rank, &lo, &hi, &rpr);
+        const int64_t nl = hi - lo;
+        std::vector<int32_t> rc_ptr(n + 1, 0);
+        for (int64_t t = 0; t < mA; ++t) rc_ptr[d_row[t] + 1]++;
+        for (int64_t i = 0; i < n; ++i) rc_ptr[i + 1] += rc_ptr[i];
+        std::vector<int32_t> rc_gid(mA);
+        std::vector<double> rc_a(mA);
+        {
+            std::vector<int32_t> fill(rc_ptr.begin(), rc_ptr.end() - 1);
+            for (int64_t t = 0; t < mA; ++t) {
+                const int32_t q = fill[d_row[t]]++;
+                rc_gid[q] = con_gid[t];
+                rc_a[q] = d_val[t];
+            }
+        }
+        const int32_t e0 = f_ptr[lo], e1 = f_ptr[hi], k0 = rc_ptr[lo], k1 = rc_ptr[hi];
+        std::vector<int32_t> lf_ptr(nl + 1), lf_col(f_col.begin() + e0, f_col.begin() + e1), lrc_ptr(nl + 1),
+            lrc_gid(rc_gid.begin() + k0, rc_gid.begin() + k1);
+        std::vector<double> lmc_val((size_t)(e1 - e0)), lrc_a(rc_a.begin() + k0, rc_a.begin() + k1);
+        for (int64_t i = 0; i <= nl; ++i) { lf_ptr[i] = f_ptr[lo + i] - e0; lrc_ptr[i] = rc_ptr[lo + i] - k0; }
+        for (int32_t e = e0; e < e1; ++e) lmc_val[e - e0] = cval[f_slot[e]];
+        TRY(dev_upload(ctx, &c.f_ptr, lf_ptr));
+        TRY(dev_upload(ctx, &c.f_col, lf_col));
+        TRY(dev_upload(ctx, &c.mc_val, lmc_val));
+        TRY(dev_upload(ctx, &c.rc_ptr, lrc_ptr));
+        TRY(dev_upload(ctx, &c.rc_gid, lrc_gid));
+        TRY(dev_upload(ctx, &c.rc_a, lrc_a));
+        c.n = nl;
+        c.row_lo = lo;
+        c.n_alloc = rpr;
+        c.m_loc = k1 - k0;
+        c.nnzF = e1 - e0;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     TRY(dev_upload(ctx, &c.pat_row, c.h_pat_row));
     TRY(dev_upload(ctx, &c.pat_col, c.h_pat_col));
     TRY(dev_upload(ctx, &c.cval, cval));
@@ -833,7 +1016,11 @@ extern "C" int lgpu_obj_scale(lgpu_ctx *ctx, double s)
         for (auto &v : ctx->lp.h_obj) v *= s;
     }
     double *lam = ctx->lam;
-    launch_map(ctx, ctx->m, [=] __device__(int64_t i) { lam[i] *= s; });
+    {
+        const Owned ow = owned(ctx);
+        const int32_t *gid = ow.gid;
+        launch_map(ctx, ow.count, [=] __device__(int64_t t) { lam[gid ? gid[t] : t] *= s; });
+    }
     ctx->cr_valid = ctx->cd_valid = false;
     CHECK_LAUNCH(ctx);
     return 0;
@@ -854,11 +1041,12 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     int64_t off = 0;
     for (int c = 0; c < ctx->ncones; ++c) {
         DevCone &cn = ctx->cones[c];
-        if (rank[c] <= 0 || rank[c] > cn.n) LGPU_FAIL(ctx, "bad rank %lld for cone %d", (long long)rank[c], c);
+        if (cn.n_glob == 0) { cn.n_glob = cn.n; cn.n_alloc = cn.n; }
+        if (rank[c] <= 0 || rank[c] > cn.n_glob) LGPU_FAIL(ctx, "bad rank %lld for cone %d", (long long)rank[c], c);
         cn.r = rank[c];
         cn.ld = (rank[c] + 3) & ~(int64_t)3;
         cn.off = off;
-        off += cn.n * cn.ld;
+        off += cn.n_alloc * cn.ld;
     }
     ctx->lp.off = off;
     off += ctx->lp.n;
@@ -869,9 +1057,14 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
               ctx->cones[0].mA == ctx->m;
     ctx->cr_valid = ctx->cd_valid = false;
     ctx->cr_updates = 0;
+    if (ctx->world > 1 && !ctx->mc) LGPU_FAIL(ctx, "partitioned runs use the fused MaxCut-type path only");
     if (ctx->mc) {
         TRY(alloc_flat(ctx, &ctx->CR));
         TRY(alloc_flat(ctx, &ctx->CD));
+    }
+    if (ctx->world > 1) {
+        dev_free(ctx->gfull);
+        TRY(dev_alloc(ctx, &ctx->gfull, (size_t)ctx->world * (size_t)ctx->N));
     }
     ctx->h = lbfgs_len;
     ctx->head = 0;
@@ -931,31 +1124,42 @@ static double *mvec_of(lgpu_ctx *ctx, int which)
 }
 
 /* host column-major n x r -> device row-major n x ld at dst */
-static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *cm, double *dst)
+/* host column-major n_glob x r -> device row-major rows [row_lo, row_lo + n) x ld at dst */
+static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *cm, double *dst, int64_t n_glob = -1,
+                         int64_t row_lo = 0)
 {
-    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
+    if (n_glob < 0) n_glob = n;
+    const size_t bytes = sizeof(double) * (size_t)n_glob * (size_t)r;
     /* straight from the caller's buffer: a pinned buffer goes by DMA, a pageable one is staged by the runtime */
     TRY(ensure_dstage(ctx, bytes));
     CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
     dim3 blk(32, 8);
-    {
+    if (n > 0) {
         Prof pr(ctx, KC_LAYOUT);
-        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, dst);
+        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, n_glob, row_lo, dst);
     }
     CHECK_LAUNCH(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); /* the caller may reuse its buffer as soon as this returns */
     return 0;
 }
-static int download_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *src, double *cm)
+/* the reverse; in a partitioned run every rank writes its rows into a zeroed full-size staging array and the
+ * arrays are summed over the ranks, so every rank returns the complete factor */
+static int download_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *src, double *cm, int64_t n_glob = -1,
+                           int64_t row_lo = 0)
 {
-    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
+    if (n_glob < 0) n_glob = n;
+    const size_t bytes = sizeof(double) * (size_t)n_glob * (size_t)r;
     TRY(ensure_dstage(ctx, bytes));
+    if (ctx->world > 1) CU(ctx, cudaMemsetAsync(ctx->dstage, 0, bytes, ctx->stream));
     dim3 blk(32, 8);
-    {
+    if (n > 0) {
         Prof pr(ctx, KC_LAYOUT);
-        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage);
+        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage, n_glob, row_lo);
     }
     CHECK_LAUNCH(ctx);
+    if (ctx->world > 1)
+        NC(ctx, g_nccl.AllReduce(ctx->dstage, ctx->dstage, (size_t)n_glob * (size_t)r, LG_NCCL_FLOAT64, LG_NCCL_SUM,
+                                 (lg_ncclComm_t)ctx->comm, ctx->stream));
     CU(ctx, cudaMemcpyAsync(cm, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -968,14 +1172,14 @@ extern "C" int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double 
     DevCone &c = ctx->cones[cone];
     if (which == LGPU_R) ctx->cr_valid = false;
     if (which == LGPU_U) ctx->cd_valid = false;
-    return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off);
+    return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off, c.n_glob, c.row_lo);
 }
 extern "C" int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *cm)
 {
     if (!ctx || !ctx->vars_ready || cone < 0 || cone >= ctx->ncones || !flat_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     DevCone &c = ctx->cones[cone];
-    return download_factor(ctx, c.n, c.r, c.ld, flat_of(ctx, which) + c.off, cm);
+    return download_factor(ctx, c.n, c.r, c.ld, flat_of(ctx, which) + c.off, cm, c.n_glob, c.row_lo);
 }
 extern "C" int lgpu_set_lp(lgpu_ctx *ctx, int which, const double *v)
 {
@@ -1005,6 +1209,19 @@ extern "C" int lgpu_get_vec(lgpu_ctx *ctx, int which, double *v)
 {
     if (!ctx || !mvec_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->world > 1 && which != LGPU_VEC_B) {
+        /* every constraint is owned by exactly one rank: owned entries into a zeroed vector, summed over the ranks */
+        double *tmp = ctx->mtmp;
+        const double *src = mvec_of(ctx, which);
+        CU(ctx, cudaMemsetAsync(tmp, 0, sizeof(double) * ctx->m, ctx->stream));
+        const Owned ow = owned(ctx);
+        const int32_t *gid = ow.gid;
+        launch_map(ctx, ow.count, [=] __device__(int64_t t) { tmp[gid[t]] = src[gid[t]]; });
+        NC(ctx, g_nccl.AllReduce(tmp, tmp, (size_t)ctx->m, LG_NCCL_FLOAT64, LG_NCCL_SUM, (lg_ncclComm_t)ctx->comm, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(v, tmp, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     CU(ctx, cudaMemcpyAsync(v, mvec_of(ctx, which), sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1026,9 +1243,10 @@ extern "C" int lgpu_fill_factor_random(lgpu_ctx *ctx, int which, uint64_t seed)
         double *p = flat_of(ctx, which) + c.off;
         const int64_t ld = c.ld, r = c.r;
         const uint64_t sd = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(c.off + 1);
+        const int64_t goff = c.row_lo * c.ld; /* element index in the whole factor: the same point for any partition */
         launch_map(ctx, c.n * c.ld, [=] __device__(int64_t i) {
             const int64_t col = i % ld;
-            uint64_t z = sd + (uint64_t)i * 0xBF58476D1CE4E5B9ull;
+            uint64_t z = sd + (uint64_t)(i + goff) * 0xBF58476D1CE4E5B9ull;
             z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
             z ^= z >> 27; z *= 0x94D049BB133111EBull;
             z ^= z >> 31;
@@ -1087,6 +1305,14 @@ extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
 /* ------------------------------------------------------------------------------------------------
  * fused MaxCut-type path helpers (ctx->mc: one diag_only cone, every constraint non-zero, no LP)
  * ------------------------------------------------------------------------------------------------*/
+/* all-gather the local rows of X into ctx->gfull (global row order) for the sparse product; one GPU: X itself */
+static const double *mc_gather(lgpu_ctx *ctx, const double *X)
+{
+    if (ctx->world <= 1) return X;
+    g_nccl.AllGather(X, ctx->gfull, (size_t)ctx->N, LG_NCCL_FLOAT64, (lg_ncclComm_t)ctx->comm, ctx->stream);
+    return ctx->gfull;
+}
+
 /* out_k = scale a_k <A_i, B_i> ; with b != nullptr also dsc[SC_PINF] = sum (b - out)^2 */
 static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double scale, double *out, bool with_pinf)
 {
@@ -1096,6 +1322,7 @@ static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double sc
     DISPATCH_G(G, k_mc_rowdot<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_rowdot<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, (int)c.ld, A, B, c.rc_ptr, c.rc_gid, c.rc_a, scale, out, with_pinf ? ctx->b : nullptr,
                       ctx->partials, ctx->counter, ctx->dsc, slot1(SC_PINF, 0)));
+    if (with_pinf) allreduce_scalars(ctx, SC_PINF, 1);
 }
 /* T = C X (no epilogue) */
 static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
@@ -1104,9 +1331,10 @@ static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
     const int G = pick_group(c.ld);
     SlotSpec<2> sp;
     sp.slot[0] = SC_TMP; sp.slot[1] = SC_TMP2; sp.accumulate = 0;
+    const double *Xg = mc_gather(ctx, X);
     Prof pr(ctx, KC_MC_SPMM);
     DISPATCH_G(G, k_mc_spmm<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
-                      c.n, c.f_ptr, c.f_col, c.mc_val, X, (int)c.ld, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      c.n, c.f_ptr, c.f_col, c.mc_val, Xg, X, (int)c.ld, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                       ctx->partials, ctx->counter, ctx->dsc, sp));
 }
 static void mc_refresh_cr(lgpu_ctx *ctx)
@@ -1125,6 +1353,7 @@ static void mc_grad(lgpu_ctx *ctx)
     DISPATCH_G(G, k_mc_grad<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_grad<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, (int)c.ld, ctx->R, ctx->CR, ctx->G, c.rc_ptr, c.rc_gid, c.rc_a, ctx->M1, ctx->partials, ctx->counter,
                       ctx->dsc, slot1(SC_LAG, 0)));
+    allreduce_scalars(ctx, SC_LAG, 1);
 }
 
 static void pair_ptrs(lgpu_ctx *ctx, int pair, double **A, double **B)
@@ -1218,7 +1447,12 @@ extern "C" int lgpu_alm_cal_grad(lgpu_ctx *ctx, double rho, double *lag_norm_squ
         /* M1 = -lambda - rho b + rho constrValSum (lorads_alm.c:38-50) */
         double *M1 = ctx->M1;
         const double *lam = ctx->lam, *b = ctx->b, *cvs = ctx->cvs;
-        launch_map(ctx, ctx->m, [=] __device__(int64_t i) { M1[i] = -lam[i] - rho * b[i] + rho * cvs[i]; });
+        const Owned ow = owned(ctx);
+        const int32_t *gid = ow.gid;
+        launch_map(ctx, ow.count, [=] __device__(int64_t t) {
+            const int64_t i = gid ? gid[t] : t;
+            M1[i] = -lam[i] - rho * b[i] + rho * cvs[i];
+        });
     }
     if (ctx->mc) mc_grad(ctx);
     else grad_from_m1(ctx);
@@ -1316,10 +1550,11 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
         const int G = pick_group(c.ld);
         SlotSpec<2> sp;
         sp.slot[0] = SC_P1; sp.slot[1] = SC_P2; sp.accumulate = 0;
+        const double *Dg = mc_gather(ctx, ctx->U);
         {
             Prof pr(ctx, KC_MC_SPMM);
             DISPATCH_G(G, k_mc_spmm<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
-                              c.n, c.f_ptr, c.f_col, c.mc_val, ctx->U, (int)c.ld, ctx->CD, ctx->R, c.rc_ptr, c.rc_gid, c.rc_a,
+                              c.n, c.f_ptr, c.f_col, c.mc_val, Dg, ctx->U, (int)c.ld, ctx->CD, ctx->R, c.rc_ptr, c.rc_gid, c.rc_a,
                               ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, sp));
         }
         ctx->cd_valid = true;
@@ -1346,7 +1581,12 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
         SlotSpec<5> sp;
         sp.slot[0] = SC_LS0; sp.slot[1] = SC_LS1; sp.slot[2] = SC_LS2; sp.slot[3] = SC_LS3; sp.slot[4] = SC_LS4;
         sp.accumulate = 0;
-        launch_reduce<5>(ctx, ctx->m, [=] __device__(int64_t i, double(&acc)[5]) {
+        const Owned ow = owned(ctx);
+        const int32_t *gid = ow.gid;
+        const int world = ctx->world;
+        ctx->world = 1; /* local sums only here: p1, p2 and the five terms are all-reduced together just below */
+        launch_reduce<5>(ctx, ow.count, [=] __device__(int64_t t, double(&acc)[5]) {
+            const int64_t i = gid ? gid[t] : t;
             const double q0 = (b[i] - cvs[i]) + rinv * lam[i];
             const double a = q1[i], c2 = q2[i];
             acc[0] = fma(c2, c2, acc[0]);
@@ -1355,6 +1595,8 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
             acc[3] = fma(a, a, acc[3]);
             acc[4] = fma(q0, a, acc[4]);
         }, sp);
+        ctx->world = world;
+        TRY(allreduce_scalars(ctx, SC_P1, 7));
     }
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_P1, 7));
@@ -1390,7 +1632,12 @@ extern "C" int lgpu_alm_step(lgpu_ctx *ctx, double tau)
         double *cvs = ctx->cvs;
         const double *q1 = ctx->q1, *q2 = ctx->q2;
         const double t2 = tau * tau;
-        launch_map(ctx, ctx->m, [=] __device__(int64_t i) { cvs[i] = fma(t2, q2[i], fma(tau, q1[i], cvs[i])); });
+        const Owned ow = owned(ctx);
+        const int32_t *gid = ow.gid;
+        launch_map(ctx, ow.count, [=] __device__(int64_t t) {
+            const int64_t i = gid ? gid[t] : t;
+            cvs[i] = fma(t2, q2[i], fma(tau, q1[i], cvs[i]));
+        });
     }
     CHECK_LAUNCH(ctx);
     return 0;
@@ -1441,11 +1688,17 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
                           c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->partials,
                           ctx->counter, ctx->dsc, sp, SC_BETA0 + ctx->head));
     }
+    if (ctx->world > 1) {
+        TRY(allreduce_scalars(ctx, SC_LAG, 3));
+        double *dsc = ctx->dsc;
+        const int ib = SC_BETA0 + ctx->head;
+        launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
+    }
     ctx->head = (ctx->head + 1) % ctx->h;
     ctx->cr_updates++;
     if (ctx->cr_updates >= 64) mc_refresh_cr(ctx); /* bound the rounding drift of the carried C R */
     CHECK_LAUNCH(ctx);
-    TRY(fetch_scalars(ctx, SC_LAG, SC_YS - SC_LAG + 1));
+    TRY(fetch_scalars(ctx, SC_LAG, 3));
     *lag_norm_square = ctx->hsc[SC_LAG];
     *pinf_l1 = sqrt(ctx->hsc[SC_PINF]) / (1.0 + ctx->b_nrm1);
     return 0;
@@ -1483,7 +1736,12 @@ extern "C" int lgpu_update_dual_var(lgpu_ctx *ctx, double rho)
     double *lam = ctx->lam;
     const double *b = ctx->b, *cvs = ctx->cvs;
     /* lambda += rho b ; lambda -= rho constrValSum (two axpys, lorads_alg_common.c:511-524) */
-    launch_map(ctx, ctx->m, [=] __device__(int64_t i) { lam[i] = fma(-rho, cvs[i], fma(rho, b[i], lam[i])); });
+    const Owned ow = owned(ctx);
+    const int32_t *gid = ow.gid;
+    launch_map(ctx, ow.count, [=] __device__(int64_t t) {
+        const int64_t i = gid ? gid[t] : t;
+        lam[i] = fma(-rho, cvs[i], fma(rho, b[i], lam[i]));
+    });
     CHECK_LAUNCH(ctx);
     return 0;
 }
@@ -1536,7 +1794,12 @@ extern "C" int lgpu_cal_dual_obj(lgpu_ctx *ctx, double *dobj)
     if (!ctx) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     const double *b = ctx->b, *lam = ctx->lam;
-    launch_reduce<1>(ctx, ctx->m, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(b[i], lam[i], acc[0]); }, slot1(SC_DOBJ));
+    const Owned ow = owned(ctx);
+    const int32_t *gid = ow.gid;
+    launch_reduce<1>(ctx, ow.count, [=] __device__(int64_t t, double(&acc)[1]) {
+        const int64_t i = gid ? gid[t] : t;
+        acc[0] = fma(b[i], lam[i], acc[0]);
+    }, slot1(SC_DOBJ));
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_DOBJ, 1));
     *dobj = ctx->hsc[SC_DOBJ];
@@ -1662,7 +1925,12 @@ static int admm_update_one(lgpu_ctx *ctx, int ci, double *upd_flat, const double
         /* single cone: constrVal_c == constrValSum ; S V = C V + Diag(A^*(M1)) V */
         double *M1 = ctx->M1;
         const double *b = ctx->b, *cvs = ctx->cvs, *lam = ctx->lam;
-        launch_map(ctx, m, [=] __device__(int64_t i) { M1[i] = rho * ((-b[i] + cvs[i]) - cvs[i]) - lam[i]; });
+        const Owned ow = owned(ctx);
+        const int32_t *gid = ow.gid;
+        launch_map(ctx, ow.count, [=] __device__(int64_t t) {
+            const int64_t i = gid ? gid[t] : t;
+            M1[i] = rho * ((-b[i] + cvs[i]) - cvs[i]) - lam[i];
+        });
         double *upd = upd_flat, *M2 = ctx->M2, *bl = ctx->bLin;
         const double *fixed = fixed_flat;
         mc_spmm_plain(ctx, fixed, M2);
@@ -1812,6 +2080,8 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
         k_gram_finish<<<nt * nt, 256, 0, ctx->stream>>>(nchunks, nt * nt, r, part, dg);
     }
     CHECK_LAUNCH(ctx);
+    if (ctx->world > 1)
+        NC(ctx, g_nccl.AllReduce(dg, dg, (size_t)r * r, LG_NCCL_FLOAT64, LG_NCCL_SUM, (lg_ncclComm_t)ctx->comm, ctx->stream));
     CU(ctx, cudaMemcpyAsync(gram, dg, gram_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1850,6 +2120,7 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
 {
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
+    if (ctx->world > 1) LGPU_FAIL(ctx, "dual infeasibility is not partitioned in this build (run it on one GPU)");
     double total = 0.0;
     /* LP part (lorads_solver.c:1404-1412): |min(c_j - a_j^T lambda, 0)| */
     if (ctx->lp.n > 0) {

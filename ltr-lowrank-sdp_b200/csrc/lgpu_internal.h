@@ -27,6 +27,8 @@ enum {
     SC_TMP2,
     SC_NEG,
     SC_LAG,    /* sum |Grad|^2 */
+    SC_YS,     /* <y, s> */
+    SC_PINF,   /* |b - A|^2        (SC_LAG, SC_YS, SC_PINF stay contiguous: one fetch / one all-reduce) */
     SC_DG,     /* <D, Grad> */
     SC_P1,     /* <C, R D^T> accumulated over cones (not yet doubled) */
     SC_P2,     /* <C, D D^T> */
@@ -35,10 +37,8 @@ enum {
     SC_LS2,    /* q0'.q2 */
     SC_LS3,    /* |q1|^2 */
     SC_LS4,    /* q0'.q1 */
-    SC_PINF,   /* |b - A|^2 */
     SC_OBJ,    /* <C, RR^T> */
     SC_DOBJ,   /* b^T lambda */
-    SC_YS,     /* <y, s> */
     SC_CG_RR,  /* r.r */
     SC_CG_PQ,  /* p.Q */
     SC_CG_ALPHA,
@@ -75,7 +75,11 @@ struct ProfRec {
 
 struct DevCone {
     /* sizes */
-    int64_t n = 0;       /* block dimension */
+    int64_t n = 0;       /* block dimension; in a row-block partitioned run: number of rows THIS rank owns */
+    int64_t n_glob = 0;  /* block dimension of the whole problem */
+    int64_t row_lo = 0;  /* first owned row */
+    int64_t n_alloc = 0; /* rows allocated per rank (= n, or ceil(n_glob / world) so that all-gather counts are equal) */
+    int64_t m_loc = 0;   /* constraints owned by this rank (partitioned) */
     int64_t mA = 0;      /* number of non-zero constraints in this block */
     int64_t nnzP = 0;    /* aggregated lower pattern */
     int64_t nnzA = 0;    /* sum_i nnz(A_i) */
@@ -151,6 +155,10 @@ struct lgpu_ctx {
     bool vars_ready = false;
     double *R = nullptr, *U = nullptr, *V = nullptr, *G = nullptr, *M2 = nullptr, *bLin = nullptr,
            *cg_r = nullptr, *cg_p = nullptr, *cg_Q = nullptr, *stage = nullptr;
+    /* row-block partition over `world` ranks (NCCL); world == 1: single GPU */
+    int rank = 0, world = 1;
+    void *comm = nullptr;     /* ncclComm_t */
+    double *gfull = nullptr;  /* [world * n_alloc * ld] all-gathered factor rows for the sparse product */
     /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */
     bool fast_enabled = true;
     bool mc = false;

@@ -339,9 +339,10 @@ __global__ void __launch_bounds__(LGPU_TPB) k_rowscale_add(int64_t n, int ld, co
     }
 }
 
-/* host column-major n x r  <->  device row-major n x ld (padding columns zeroed) */
+/* host column-major (cm_ld rows, this rank's rows start at cm_row0)  <->  device row-major n x ld (padding columns
+ * zeroed) */
 __global__ void __launch_bounds__(LGPU_TPB) k_col2row(int64_t n, int r, int ld, const double *__restrict__ cm,
-                                                      double *__restrict__ rm)
+                                                      int64_t cm_ld, int64_t cm_row0, double *__restrict__ rm)
 {
     __shared__ double tile[32][33];
     const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_col2row(int64_t n, int r, int ld, 
         for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
             const int64_t row = row0 + threadIdx.x;
             const int col = c0 + cc;
-            tile[cc][threadIdx.x] = (row < n && col < r) ? cm[(size_t)col * n + row] : 0.0;
+            tile[cc][threadIdx.x] = (row < n && col < r) ? cm[(size_t)col * cm_ld + cm_row0 + row] : 0.0;
         }
         __syncthreads();
         for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_col2row(int64_t n, int r, int ld, 
 }
 
 __global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, const double *__restrict__ rm,
-                                                      double *__restrict__ cm)
+                                                      double *__restrict__ cm, int64_t cm_ld, int64_t cm_row0)
 {
     __shared__ double tile[32][33];
     const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, 
         for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
             const int64_t row = row0 + threadIdx.x;
             const int col = c0 + cc;
-            if (row < n && col < r) cm[(size_t)col * n + row] = tile[threadIdx.x][cc];
+            if (row < n && col < r) cm[(size_t)col * cm_ld + cm_row0 + row] = tile[threadIdx.x][cc];
         }
         __syncthreads();
     }
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
  * ================================================================================================*/
 
 /* T = C X over the full symmetric CSR with C's values stored per CSR entry.
+ * X is indexed by GLOBAL row (the all-gathered factor in a partitioned run), Xl / Rm / T by this rank's rows.
  * EPI: also q1_k = 2 a_k <R_i, X_i>, q2_k = a_k <X_i, X_i> for the constraints k of row i and the two
  * objective terms sum_i <R_i, T_i> (p1/2) and sum_i <X_i, T_i> (p2)
  *     reference: ALMCalq12p12 -> LORADSObjConstrValAll -> LORADSUVt/objAUV/coneAUV, lorads_alm.c:714-734,
@@ -469,7 +471,8 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
 template <int G, bool EPI>
 __global__ void __launch_bounds__(LGPU_TPB) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
                                                       const int32_t *__restrict__ fcol, const double *__restrict__ fval,
-                                                      const double *__restrict__ X, int ld, double *__restrict__ T,
+                                                      const double *__restrict__ X, const double *__restrict__ Xl, int ld,
+                                                      double *__restrict__ T,
                                                       const double *__restrict__ Rm, const int32_t *__restrict__ rcptr,
                                                       const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
                                                       double *__restrict__ q1, double *__restrict__ q2, double *partials,
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_spmm(int64_t n, const int32_t *
                     reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
                     if (EPI) {
                         const double2 r = reinterpret_cast<const double2 *>(Rm + (size_t)i * ld)[c];
-                        const double2 d = reinterpret_cast<const double2 *>(X + (size_t)i * ld)[c];
+                        const double2 d = reinterpret_cast<const double2 *>(Xl + (size_t)i * ld)[c];
                         rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
                         dd = fma(d.x, d.x, dd); dd = fma(d.y, d.y, dd);
                         red[0] = fma(r.x, acc.x, red[0]); red[0] = fma(r.y, acc.y, red[0]);

@@ -83,6 +83,9 @@ def lib() -> ctypes.CDLL:
         "lgpu_profile_read": (i, [_vp, i, _c_dp, _c_lp]),
         "lgpu_profile_num_classes": (i, []),
         "lgpu_profile_class_name": (ctypes.c_char_p, [i]),
+        "lgpu_partition_rows": (i, [i64, i, i, _c_lp, _c_lp, _c_lp]),
+        "lgpu_nccl_unique_id": (i, [ctypes.c_char_p]),
+        "lgpu_comm_init": (i, [_vp, ctypes.c_char_p, i, i]),
         "lgpu_set_problem": (i, [_vp, i64, _c_dp, i, _c_lp, i64]),
         "lgpu_cone_upload": (i, [_vp, i, _c_lp, _c_lp, _c_dp]),
         "lgpu_lp_upload": (i, [_vp, _c_lp, _c_lp, _c_dp]),
@@ -190,6 +193,21 @@ class SdpaProblem:
         return len(self.dims)
 
 
+def partition_rows(n: int, world: int, rank: int):
+    """(lo, hi, rows_per_rank) of the row block rank `rank` owns -- host logic, no GPU needed"""
+    lo, hi, rpr = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    if lib().lgpu_partition_rows(int(n), int(world), int(rank), ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(rpr)) != 0:
+        raise LoradsError("bad partition arguments")
+    return lo.value, hi.value, rpr.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    if lib().lgpu_nccl_unique_id(buf) != 0:
+        raise LoradsError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
 def read_sdpa(path: str) -> SdpaProblem:
     """Parse a .dat-s file with the C host reader (csrc/host/sdpa_reader.c)."""
     H = host_lib()
@@ -239,6 +257,11 @@ class Context:
         self.dims: List[int] = []
         self.nlp = 0
         self.rank: List[int] = []
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """join the NCCL communicator of a row-block partitioned run (before load())"""
+        assert len(unique_id) == 128
+        self._ck(self._L.lgpu_comm_init(self._h, unique_id, int(rank), int(world)), "lgpu_comm_init")
 
     def close(self):
         if getattr(self, "_h", None):

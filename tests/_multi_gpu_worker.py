@@ -1,0 +1,97 @@
+"""Worker for tests/test_gpu_multi.py: torchrun, one rank per GPU.  The row-block partitioned run must reproduce the
+single-GPU run of the same problem: ALM inner iterations, objective, dual update, one ADMM sweep."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ltr-lowrank-sdp_b200"))
+import lorads_b200 as lb  # noqa: E402
+
+
+def line_search(H, rho, terms):
+    tau = ctypes.c_double(0.0)
+    H.lh_line_search(float(rho), terms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(tau))
+    return tau.value
+
+
+def run(ctx, p, R0, rho, r, iters):
+    H = lb.host_lib()
+    ctx.load(p)
+    ctx.alloc_vars([r], 2)
+    ctx.set_factor(lb.R, 0, R0)
+    ctx.init_constr_val(lb.PAIR_RR)
+    ctx.alm_cal_grad(rho)
+    hist = []
+    for it in range(iters):
+        ctx.lbfgs_direction(it)
+        terms = ctx.alm_linesearch_terms(rho)
+        tau = line_search(H, rho, terms)
+        lag, pinf = ctx.alm_inner_update(rho, tau)
+        hist.append((tau, lag, pinf, terms[0], terms[1]))
+    obj = ctx.cal_obj(False)
+    ctx.update_dual_var(rho)
+    dobj = ctx.cal_dual_obj()
+    lag2 = ctx.alm_cal_grad(rho)
+    Rf = ctx.get_factor(lb.R, 0)
+    lam = ctx.get_vec(lb.VEC_DUAL)
+    cvs = ctx.get_vec(lb.VEC_CONSTR_SUM)
+    gram = ctx.gram(1, 0)
+    ctx.alm_to_admm()
+    ctx.init_constr_val(lb.PAIR_UV)
+    cg = ctx.admm_update_var(10 * rho, 1e-8, 800, 0)
+    Uf = ctx.get_factor(lb.U, 0)
+    objA = ctx.cal_obj(True)
+    return dict(hist=np.array(hist), obj=obj, dobj=dobj, lag2=lag2, R=Rf, lam=lam, cvs=cvs, gram=gram, cg=cg, U=Uf, objA=objA)
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl")
+    n, r, iters = 20001, 20, 25          # odd n: ragged last row block
+    ei, ej, w = lb.random_graph(n, 5, 3)
+    p = lb.maxcut_problem(n, ei, ej, w)
+    rng = np.random.default_rng(925)
+    R0 = rng.random((n, r)) - rng.random((n, r))
+    rho = 1.0 / np.sqrt(n)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(lb.nccl_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(uid, 0)
+    ctx = lb.Context(local)
+    ctx.comm_init(bytes(uid.numpy().tobytes()), rank, world)
+    part = run(ctx, p, R0, rho, r, iters)
+    ctx.close()
+    ok = True
+    if rank == 0:
+        one = run(lb.Context(local), p, R0, rho, r, iters)
+        h1, hp = one["hist"], part["hist"]
+        err_hist = float(np.max(np.abs(hp - h1) / np.maximum(np.abs(h1), 1e-30)))
+        checks = {"hist": err_hist < 1e-8, "obj": abs(part["obj"] - one["obj"]) <= 1e-10 * abs(one["obj"]),
+                  "dobj": abs(part["dobj"] - one["dobj"]) <= 1e-9 * max(abs(one["dobj"]), 1e-12),
+                  "lag2": abs(part["lag2"] - one["lag2"]) <= 1e-8 * one["lag2"], "R": rel(part["R"], one["R"]) < 1e-9,
+                  "lam": rel(part["lam"], one["lam"]) < 1e-9, "cvs": rel(part["cvs"], one["cvs"]) < 1e-9,
+                  "gram": rel(part["gram"], one["gram"]) < 1e-10, "cg": abs(part["cg"] - one["cg"]) <= max(2, 0.05 * one["cg"]),
+                  "U": rel(part["U"], one["U"]) < 1e-6, "objA": abs(part["objA"] - one["objA"]) <= 1e-8 * abs(one["objA"])}
+        ok = all(checks.values())
+        print("MULTI_GPU_CHECKS", checks, "hist_err", err_hist, "cg", part["cg"], one["cg"], flush=True)
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_OK" if ok else "MULTI_GPU_FAIL", flush=True)
+    sys.exit(0 if int(flag[0]) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
