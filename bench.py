@@ -144,12 +144,12 @@ def algorithmic_bytes(cls, info, n, ld, m, share=1.0):
         return 16.0 * nnzP + F * (4.0 / 3.0)
     if cls == "k_spmm":
         return 8.0 * nnzF + 8.0 * nnzP + 4.0 * (n + 1) + 2 * F
-    if cls == "k_mc_spmm":   # CSR + own rows of R, D + T written; a partitioned rank also reads the other ranks' D rows once
-        return 12.0 * nnzF + 4.0 * (n * share + 1) + 3 * F + 16.0 * m + 8.0 * n * ld * (1.0 - share)
-    if cls == "k_mc_step":
-        return 10 * F + 56.0 * m
-    if cls == "k_mc_dir":    # five fused passes: 13 F read + 4 F written over 5 launches
-        return 17 * F / 5.0
+    if cls == "k_mc_spmm":   # CSR (col + value) + every row of D once + T written (a partitioned rank reads all of D)
+        return 12.0 * nnzF + 4.0 * (n * share + 1) + 8.0 * n * ld + F
+    if cls == "k_mc_step":   # reads R, D, CR, T, G, s_old, y_old ; writes R, CR, G, s_new, y_new ; m-vectors
+        return 12 * F + 56.0 * m
+    if cls == "k_mc_dir":    # direction pass: reads G, s0, y0, s1, y1, R, CR ; writes D, q1, q2
+        return 8 * F + 16.0 * m
     if cls == "k_wsum":
         return 12.0 * info["nnzA"] + 8.0 * m + 16.0 * nnzP
     if cls == "k_gather":

@@ -96,6 +96,11 @@ int lgpu_alloc_vars(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len);
  * lgpu_alloc_vars / lgpu_aug_rank.  lgpu_uses_fused_path reports what the current variables use. */
 int lgpu_set_fused_path(lgpu_ctx *ctx, int on);
 int lgpu_uses_fused_path(const lgpu_ctx *ctx);
+/* On the fused path with the default history length 2 the L-BFGS scalars (alpha, beta <y,q>, <D,Grad>) are formed
+ * from inner products carried from the step pass instead of by the recursion's own four passes; the direction then
+ * costs one pass.  Same operations on the same numbers up to the rounding of those inner products.  Switch
+ * (default 1) for A/B parity tests. */
+int lgpu_set_carried_dots(lgpu_ctx *ctx, int on);
 int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double *colmajor);
 int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *colmajor);
 int lgpu_set_lp(lgpu_ctx *ctx, int which, const double *v);

@@ -148,7 +148,7 @@ template <class F> static void launch_scalar(lgpu_ctx *ctx, F f);
 template <int K, class F, class P>
 static void launch_reduce_post(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec, P post, int cls = KC_REDUCE)
 {
-    if (ctx->world > 1) {
+    if (ctx->world > 1 && !ctx->defer_allreduce) {
         {
             Prof pr(ctx, cls);
             k_reduce<K, F, NoPost><<<grid_for(ctx, n > 0 ? n : 1, (const void *)k_reduce<K, F, NoPost>), LGPU_TPB, 0, ctx->stream>>>(
@@ -417,7 +417,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->dsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->hsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
-        cudaMalloc((void **)&ctx->partials, sizeof(double) * 8 * LGPU_MAX_PARTIAL_BLOCKS) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->partials, sizeof(double) * LGPU_MAX_REDUCE * LGPU_MAX_PARTIAL_BLOCKS) != cudaSuccess ||
         cudaMalloc((void **)&ctx->counter, sizeof(unsigned int)) != cudaSuccess) {
         g_create_err = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx;
@@ -1057,6 +1057,9 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
               ctx->cones[0].mA == ctx->m;
     ctx->cr_valid = ctx->cd_valid = false;
     ctx->cr_updates = 0;
+    ctx->gram_valid = false;
+    ctx->gram_pair_ok[0] = ctx->gram_pair_ok[1] = false;
+    ctx->epi_done = false;
     if (ctx->world > 1 && !ctx->mc) LGPU_FAIL(ctx, "partitioned runs use the fused MaxCut-type path only");
     if (ctx->mc) {
         TRY(alloc_flat(ctx, &ctx->CR));
@@ -1086,6 +1089,15 @@ extern "C" int lgpu_set_fused_path(lgpu_ctx *ctx, int on)
     return 0;
 }
 extern "C" int lgpu_uses_fused_path(const lgpu_ctx *ctx) { return (ctx && ctx->mc) ? 1 : 0; }
+/* A/B switch: carried inner products for the L-BFGS scalars (default on) vs the two-loop recursion's own passes */
+extern "C" int lgpu_set_carried_dots(lgpu_ctx *ctx, int on)
+{
+    if (!ctx) return 1;
+    ctx->gram_enabled = on != 0;
+    ctx->gram_valid = false;
+    ctx->gram_pair_ok[0] = ctx->gram_pair_ok[1] = false;
+    return 0;
+}
 
 extern "C" int lgpu_alloc_vars(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
 {
@@ -1171,7 +1183,7 @@ extern "C" int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double 
     CU(ctx, cudaSetDevice(ctx->device));
     DevCone &c = ctx->cones[cone];
     if (which == LGPU_R) ctx->cr_valid = false;
-    if (which == LGPU_U) ctx->cd_valid = false;
+    if (which == LGPU_U) { ctx->cd_valid = false; ctx->epi_done = false; }
     return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off, c.n_glob, c.row_lo);
 }
 extern "C" int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *cm)
@@ -1238,7 +1250,7 @@ extern "C" int lgpu_fill_factor_random(lgpu_ctx *ctx, int which, uint64_t seed)
     if (!ctx || !ctx->vars_ready || !flat_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     if (which == LGPU_R) ctx->cr_valid = false;
-    if (which == LGPU_U) ctx->cd_valid = false;
+    if (which == LGPU_U) { ctx->cd_valid = false; ctx->epi_done = false; }
     for (auto &c : ctx->cones) {
         double *p = flat_of(ctx, which) + c.off;
         const int64_t ld = c.ld, r = c.r;
@@ -1324,18 +1336,15 @@ static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double sc
                       ctx->partials, ctx->counter, ctx->dsc, slot1(SC_PINF, 0)));
     if (with_pinf) allreduce_scalars(ctx, SC_PINF, 1);
 }
-/* T = C X (no epilogue) */
+/* T = C X ; X local rows (all-gathered first in a partitioned run) */
 static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
 {
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
-    SlotSpec<2> sp;
-    sp.slot[0] = SC_TMP; sp.slot[1] = SC_TMP2; sp.accumulate = 0;
     const double *Xg = mc_gather(ctx, X);
     Prof pr(ctx, KC_MC_SPMM);
-    DISPATCH_G(G, k_mc_spmm<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
-                      c.n, c.f_ptr, c.f_col, c.mc_val, Xg, X, (int)c.ld, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                      ctx->partials, ctx->counter, ctx->dsc, sp));
+    DISPATCH_G(G, k_mc_spmm<GG, 2><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2>), LGPU_TPB, 0, ctx->stream>>>(
+                      c.n, c.f_ptr, c.f_col, c.mc_val, Xg, (int)c.ld, T));
 }
 static void mc_refresh_cr(lgpu_ctx *ctx)
 {
@@ -1459,6 +1468,76 @@ extern "C" int lgpu_alm_cal_grad(lgpu_ctx *ctx, double rho, double *lag_norm_squ
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_LAG, 1));
     *lag_norm_square = ctx->hsc[SC_LAG];
+    ctx->gram.gg = ctx->hsc[SC_LAG];
+    ctx->gram_valid = false; /* the gradient changed outside a step: <g, s_j>, <g, y_j> are stale */
+    return 0;
+}
+
+/* L-BFGS direction of the fused path with history length 2: the two-loop recursion's scalars come from carried
+ * inner products (formed by the step pass, or by one refresh pass when the gradient was recomputed outside a step),
+ * so the direction costs ONE pass that also produces q1, q2 and <C, R D^T>.
+ * reference: LBFGSDirection + LBFGSDirectionUseGrad, lorads_alm.c:347-508,607-627 */
+static int mc_direction_gram(lgpu_ctx *ctx, int nn)
+{
+    DevCone &c = ctx->cones[0];
+    const int h = 2;
+    const int j1 = (ctx->head - 1 + h) % h, j0 = j1 ^ 1;
+    auto &gm = ctx->gram;
+    const bool have = ctx->gram_valid && ctx->gram_pair_ok[j1] && (nn < 2 || ctx->gram_pair_ok[j0]);
+    if (nn > 0 && !have) {
+        /* refresh: ten inner products in one pass over (G, s0, y0, s1, y1) */
+        const double *G = ctx->G, *s1 = ctx->s[j1], *y1 = ctx->y[j1], *s0 = ctx->s[j0], *y0 = ctx->y[j0];
+        SlotSpec<10> sp;
+        for (int k = 0; k < 10; ++k) sp.slot[k] = SC_GSN + k;
+        sp.accumulate = 0;
+        launch_reduce_post<10>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[10]) {
+            const double g = G[i], a = s1[i], b = y1[i], p = s0[i], q = y0[i];
+            acc[0] = fma(g, a, acc[0]); acc[1] = fma(g, b, acc[1]); acc[2] = fma(g, p, acc[2]); acc[3] = fma(g, q, acc[3]);
+            acc[4] = fma(p, b, acc[4]); acc[5] = fma(q, b, acc[5]); acc[6] = fma(b, b, acc[6]); acc[7] = fma(q, q, acc[7]);
+            acc[8] = fma(b, a, acc[8]); acc[9] = fma(q, p, acc[9]);
+        }, sp, NoPost(), KC_MC_DIR);
+        CHECK_LAUNCH(ctx);
+        TRY(fetch_scalars(ctx, SC_GSN, 10));
+        const double *v = ctx->hsc + SC_GSN;
+        gm.sg[j1] = v[0]; gm.yg[j1] = v[1]; gm.sg[j0] = v[2]; gm.yg[j0] = v[3];
+        gm.so_yn = v[4]; gm.yo_yn = v[5]; gm.yy[j1] = v[6]; gm.yy[j0] = v[7];
+        gm.beta[j1] = 1.0 / v[8]; gm.beta[j0] = 1.0 / v[9];
+        ctx->gram_valid = true;
+        ctx->gram_pair_ok[0] = ctx->gram_pair_ok[1] = true;
+    }
+    DirCoef cf;
+    cf.a1 = cf.a0 = cf.w0 = cf.w1 = 0.0;
+    cf.nn = nn;
+    if (nn >= 1) {
+        /* the recursion's scalars, in the reference's order of operations */
+        double dg;
+        cf.a1 = gm.beta[j1] * gm.sg[j1];
+        if (nn == 1) {
+            const double t1 = gm.yg[j1] - cf.a1 * gm.yy[j1];
+            cf.w1 = cf.a1 - gm.beta[j1] * t1;
+            dg = -(gm.gg - cf.a1 * gm.yg[j1] + cf.w1 * gm.sg[j1]);
+        } else {
+            cf.a0 = gm.beta[j0] * (gm.sg[j0] - cf.a1 * gm.so_yn);
+            const double t0 = gm.yg[j0] - cf.a1 * gm.yo_yn - cf.a0 * gm.yy[j0];
+            cf.w0 = cf.a0 - gm.beta[j0] * t0;
+            const double t1 = gm.yg[j1] - cf.a1 * gm.yy[j1] - cf.a0 * gm.yo_yn + cf.w0 * gm.so_yn;
+            cf.w1 = cf.a1 - gm.beta[j1] * t1;
+            dg = -(gm.gg - cf.a1 * gm.yg[j1] - cf.a0 * gm.yg[j0] + cf.w0 * gm.sg[j0] + cf.w1 * gm.sg[j1]);
+        }
+        if (!(dg < 0.0)) cf.nn = 0; /* <D, Grad> >= 0 (or NaN): fall back to D = -Grad */
+    }
+    if (!ctx->cr_valid) mc_refresh_cr(ctx);
+    const int G = pick_group(c.ld);
+    ctx->defer_allreduce = true; /* <C R, D> joins the seven line-search terms' all-reduce */
+    {
+        Prof pr(ctx, KC_MC_DIR);
+        DISPATCH_G(G, k_mc_combine<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG>), LGPU_TPB, 0, ctx->stream>>>(
+                          c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], ctx->R, ctx->CR, ctx->U, c.rc_ptr,
+                          c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0)));
+    }
+    ctx->defer_allreduce = false;
+    ctx->epi_done = true;
+    CHECK_LAUNCH(ctx);
     return 0;
 }
 
@@ -1471,13 +1550,15 @@ extern "C" int lgpu_lbfgs_direction(lgpu_ctx *ctx, int64_t inner_iter)
     const double *G = ctx->G;
     double *dsc = ctx->dsc;
     ctx->cd_valid = false;
+    ctx->epi_done = false;
+    const int h = ctx->h;
+    const int nn = (int)((inner_iter <= (ctx->lp.n > 0 ? h : h - 1)) ? inner_iter : h); /* Q4: LP variant uses <= h */
+    if (ctx->mc && ctx->gram_enabled && h == 2) return mc_direction_gram(ctx, nn);
     if (inner_iter == 0) {
         launch_map(ctx, N, [=] __device__(int64_t i) { D[i] = -G[i]; });
         CHECK_LAUNCH(ctx);
         return 0; /* the reference returns before the <D,Grad> test changes anything: D = -Grad already */
     }
-    const int h = ctx->h;
-    const int nn = (int)((inner_iter <= (ctx->lp.n > 0 ? h : h - 1)) ? inner_iter : h); /* Q4: LP variant uses <= h */
     /* two-loop recursion (lorads_alm.c:468-505) as 2 nn + 1 fused passes: every pass applies the previous axpy and
      * accumulates the next dot product; the derived scalar (alpha or alpha - beta <y,q>) is formed by the pass's
      * finishing thread.  Same operations in the same order as the plain recursion. */
@@ -1545,18 +1626,25 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
     CU(ctx, cudaSetDevice(ctx->device));
     double *dsc = ctx->dsc;
     if (ctx->mc) {
-        /* one sparse product T = C D with the q1/q2/p1/p2 epilogue */
+        /* one sparse product T = C D; then q1, q2, p1, p2.  If the direction pass already produced q1, q2 and
+         * <C, R D^T> = <C R, D> (carried inner products), only p2 = <D, T> is left. */
         DevCone &c = ctx->cones[0];
         const int G = pick_group(c.ld);
-        SlotSpec<2> sp;
-        sp.slot[0] = SC_P1; sp.slot[1] = SC_P2; sp.accumulate = 0;
-        const double *Dg = mc_gather(ctx, ctx->U);
-        {
-            Prof pr(ctx, KC_MC_SPMM);
-            DISPATCH_G(G, k_mc_spmm<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
-                              c.n, c.f_ptr, c.f_col, c.mc_val, Dg, ctx->U, (int)c.ld, ctx->CD, ctx->R, c.rc_ptr, c.rc_gid, c.rc_a,
-                              ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, sp));
+        mc_spmm_plain(ctx, ctx->U, ctx->CD);
+        ctx->defer_allreduce = true; /* local sums: p1, p2 and the five terms are all-reduced together below */
+        if (ctx->epi_done) {
+            const double *D = ctx->U, *T = ctx->CD;
+            launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(D[i], T[i], acc[0]); },
+                             slot1(SC_P2));
+        } else {
+            SlotSpec<2> sp;
+            sp.slot[0] = SC_P1; sp.slot[1] = SC_P2; sp.accumulate = 0;
+            Prof pr(ctx, KC_GATHER);
+            DISPATCH_G(G, k_mc_epi<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_epi<GG>), LGPU_TPB, 0, ctx->stream>>>(
+                              c.n, (int)c.ld, ctx->R, ctx->U, ctx->CD, c.rc_ptr, c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials,
+                              ctx->counter, ctx->dsc, sp));
         }
+        ctx->defer_allreduce = false;
         ctx->cd_valid = true;
     } else {
     launch_scalar(ctx, [=] __device__() { dsc[SC_P1] = 0.0; dsc[SC_P2] = 0.0; });
@@ -1583,8 +1671,7 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
         sp.accumulate = 0;
         const Owned ow = owned(ctx);
         const int32_t *gid = ow.gid;
-        const int world = ctx->world;
-        ctx->world = 1; /* local sums only here: p1, p2 and the five terms are all-reduced together just below */
+        ctx->defer_allreduce = true;
         launch_reduce<5>(ctx, ow.count, [=] __device__(int64_t t, double(&acc)[5]) {
             const int64_t i = gid ? gid[t] : t;
             const double q0 = (b[i] - cvs[i]) + rinv * lam[i];
@@ -1595,7 +1682,7 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
             acc[3] = fma(a, a, acc[3]);
             acc[4] = fma(q0, a, acc[4]);
         }, sp);
-        ctx->world = world;
+        ctx->defer_allreduce = false;
         TRY(allreduce_scalars(ctx, SC_P1, 7));
     }
     CHECK_LAUNCH(ctx);
@@ -1659,7 +1746,9 @@ extern "C" int lgpu_lbfgs_push(lgpu_ctx *ctx, double tau)
     }, slot1(SC_YS));
     const int ib = SC_BETA0 + ctx->head;
     launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
+    ctx->gram_pair_ok[ctx->head] = false;
     ctx->head = (ctx->head + 1) % ctx->h;
+    ctx->gram_valid = false;
     CHECK_LAUNCH(ctx);
     return 0;
 }
@@ -1679,28 +1768,54 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
     }
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
-    SlotSpec<3> sp;
-    sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
-    {
+    const bool gram = ctx->gram_enabled && ctx->h == 2;
+    const int jn = ctx->head, jo = (ctx->head + 1) % ctx->h;
+    if (gram) {
+        SlotSpec<10> sp;
+        for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
+        sp.accumulate = 0;
         Prof pr(ctx, KC_MC_STEP);
-        DISPATCH_G(G, k_mc_step<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG>), LGPU_TPB, 0, ctx->stream>>>(
-                          c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[ctx->head], ctx->y[ctx->head],
-                          c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->partials,
-                          ctx->counter, ctx->dsc, sp, SC_BETA0 + ctx->head));
+        DISPATCH_G(G, k_mc_step<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
+                          c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid,
+                          c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo], ctx->partials,
+                          ctx->counter, ctx->dsc, sp, SC_BETA0 + jn));
+    } else {
+        SlotSpec<3> sp;
+        sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
+        Prof pr(ctx, KC_MC_STEP);
+        DISPATCH_G(G, k_mc_step<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
+                          c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid,
+                          c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials,
+                          ctx->counter, ctx->dsc, sp, SC_BETA0 + jn));
     }
+    const int nsc = gram ? 10 : 3;
     if (ctx->world > 1) {
-        TRY(allreduce_scalars(ctx, SC_LAG, 3));
+        TRY(allreduce_scalars(ctx, SC_LAG, nsc));
         double *dsc = ctx->dsc;
-        const int ib = SC_BETA0 + ctx->head;
+        const int ib = SC_BETA0 + jn;
         launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
     }
     ctx->head = (ctx->head + 1) % ctx->h;
     ctx->cr_updates++;
+    ctx->cd_valid = false;
+    ctx->epi_done = false;
     if (ctx->cr_updates >= 64) mc_refresh_cr(ctx); /* bound the rounding drift of the carried C R */
     CHECK_LAUNCH(ctx);
-    TRY(fetch_scalars(ctx, SC_LAG, 3));
+    TRY(fetch_scalars(ctx, SC_LAG, nsc));
     *lag_norm_square = ctx->hsc[SC_LAG];
     *pinf_l1 = sqrt(ctx->hsc[SC_PINF]) / (1.0 + ctx->b_nrm1);
+    if (gram) {
+        auto &gm = ctx->gram;
+        const double *v = ctx->hsc;
+        gm.gg = v[SC_LAG];
+        gm.beta[jn] = 1.0 / v[SC_YS];
+        gm.sg[jn] = v[SC_GSN]; gm.yg[jn] = v[SC_GYN]; gm.sg[jo] = v[SC_GSO]; gm.yg[jo] = v[SC_GYO];
+        gm.so_yn = v[SC_SOYN]; gm.yo_yn = v[SC_YOYN]; gm.yy[jn] = v[SC_YNYN];
+        ctx->gram_pair_ok[jn] = true;
+        /* <g, .> is fresh for both pairs; the older pair's <y,y> and beta are carried from the step that formed it
+         * (gram_pair_ok); otherwise the next two-pair direction refreshes everything in one pass */
+        ctx->gram_valid = true;
+    }
     return 0;
 }
 
@@ -1813,6 +1928,7 @@ extern "C" int lgpu_alm_to_admm(lgpu_ctx *ctx)
     CU(ctx, cudaMemcpyAsync(ctx->V, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ctx->U, ctx->R, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->cd_valid = false;
+    ctx->epi_done = false;
     return 0;
 }
 extern "C" int lgpu_copy_r_to_v(lgpu_ctx *ctx)
@@ -2036,6 +2152,7 @@ extern "C" int lgpu_admm_update_var(lgpu_ctx *ctx, double rho, double cg_tol, in
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     ctx->cd_valid = false;
+    ctx->epi_done = false;
     for (int ci = 0; ci < ctx->ncones; ++ci) {
         DevCone &c = ctx->cones[ci];
         int64_t it = 0;

@@ -20,6 +20,7 @@
 
 #define LGPU_NSCALAR 256
 #define LGPU_MAX_PARTIAL_BLOCKS 1184 /* 148 SMs x 8 resident CTAs of 256 threads */
+#define LGPU_MAX_REDUCE 12           /* widest fused reduction (k_reduce / grid_reduce_finish) */
 
 /* device scalar slots (ctx->dsc) */
 enum {
@@ -28,7 +29,17 @@ enum {
     SC_NEG,
     SC_LAG,    /* sum |Grad|^2 */
     SC_YS,     /* <y, s> */
-    SC_PINF,   /* |b - A|^2        (SC_LAG, SC_YS, SC_PINF stay contiguous: one fetch / one all-reduce) */
+    SC_PINF,   /* |b - A|^2        (SC_LAG .. SC_YNYN stay contiguous: one fetch / one all-reduce) */
+    SC_GSN,    /* carried L-BFGS inner products (history length 2): <g, s_new> */
+    SC_GYN,    /* <g, y_new> */
+    SC_GSO,    /* <g, s_old> */
+    SC_GYO,    /* <g, y_old> */
+    SC_SOYN,   /* <s_old, y_new> */
+    SC_YOYN,   /* <y_old, y_new> */
+    SC_YNYN,   /* <y_new, y_new> */
+    SC_YOYO,   /* <y_old, y_old> (refresh pass only) */
+    SC_BN,     /* refresh pass only: <y_new, s_new>, <y_old, s_old> */
+    SC_BO,
     SC_DG,     /* <D, Grad> */
     SC_P1,     /* <C, R D^T> accumulated over cones (not yet doubled) */
     SC_P2,     /* <C, D D^T> */
@@ -165,6 +176,15 @@ struct lgpu_ctx {
     double *CR = nullptr, *CD = nullptr;
     bool cr_valid = false, cd_valid = false;
     int cr_updates = 0;
+    /* carried inner products of the two L-BFGS pairs and the current gradient (fused path, history length 2) */
+    bool gram_enabled = true;
+    bool gram_valid = false;
+    bool gram_pair_ok[2] = {false, false};
+    bool defer_allreduce = false; /* partitioned: keep local sums, a later call all-reduces the whole pack */
+    struct {
+        double gg, sg[2], yg[2], yy[2], beta[2], so_yn, yo_yn; /* indexed by ring slot; cross terms: (older, newer) */
+    } gram;
+    bool epi_done = false; /* q1, q2 and <C, R D^T> already produced by the direction pass for the current D */
     int h = 0, head = 0;
     std::vector<double *> s, y;
     std::vector<int64_t> cg_last_iter; /* per cone: cg->iter persists across calls (reference quirk) */
@@ -172,7 +192,7 @@ struct lgpu_ctx {
     /* scalars and reduction scratch */
     double *dsc = nullptr;      /* device scalars */
     double *hsc = nullptr;      /* pinned host mirror */
-    double *partials = nullptr; /* [8 * LGPU_MAX_PARTIAL_BLOCKS] */
+    double *partials = nullptr; /* [LGPU_MAX_REDUCE * LGPU_MAX_PARTIAL_BLOCKS] */
     unsigned int *counter = nullptr;
     /* live per-launch timing */
     bool prof = false;

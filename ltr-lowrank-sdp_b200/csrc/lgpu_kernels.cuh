@@ -462,21 +462,59 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
  * constraints per row are handled; MaxCut has exactly one.
  * ================================================================================================*/
 
-/* T = C X over the full symmetric CSR with C's values stored per CSR entry.
- * X is indexed by GLOBAL row (the all-gathered factor in a partitioned run), Xl / Rm / T by this rank's rows.
- * EPI: also q1_k = 2 a_k <R_i, X_i>, q2_k = a_k <X_i, X_i> for the constraints k of row i and the two
- * objective terms sum_i <R_i, T_i> (p1/2) and sum_i <X_i, T_i> (p2)
+/* T = C X over the full symmetric CSR with C's values stored per CSR entry; X is indexed by GLOBAL row (the
+ * all-gathered factor in a partitioned run), T by this rank's rows.       reference: mul_rk, lorads_sdp_data.c:750-763 */
+/* Measured on B200 (profiles/r1_spmm_variants.md): this gather is bound by DRAM, and what keeps DRAM busy is resident
+ * warps, not per-thread tricks -- the same product with a software-pipelined (column, value) prefetch and 8 loads in
+ * flight per lane needed 48-115 registers and ran 1.8-3.9x slower than this 32-register form at 8 CTAs per SM.
+ * A group of G lanes owns a row; lane c holds 16-byte column word c; U entries are fetched per trip. */
+template <int G, int U>
+__global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
+                                                                const int32_t *__restrict__ fcol,
+                                                                const double *__restrict__ fval, const double *__restrict__ X,
+                                                                int ld, double *__restrict__ T)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    for (int64_t i = g0; i < n; i += groups) {
+        const int e0 = fptr[i], e1 = fptr[i + 1];
+        for (int c = lane; c < ld2; c += G) {
+            double2 acc = make_double2(0.0, 0.0);
+            int e = e0;
+            for (; e + U <= e1; e += U) {
+                double2 x[U];
+                double v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    v[u] = fval[e + u];
+                    x[u] = reinterpret_cast<const double2 *>(X + (size_t)fcol[e + u] * ld)[c];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { acc.x = fma(v[u], x[u].x, acc.x); acc.y = fma(v[u], x[u].y, acc.y); }
+            }
+            for (; e < e1; ++e) {
+                const double v = fval[e];
+                const double2 x = reinterpret_cast<const double2 *>(X + (size_t)fcol[e] * ld)[c];
+                acc.x = fma(v, x.x, acc.x); acc.y = fma(v, x.y, acc.y);
+            }
+            reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
+        }
+    }
+}
+
+/* Row-local pass after T = C D: q1_k = 2 a_k <R_i, D_i>, q2_k = a_k <D_i, D_i> for the constraints k of row i, and the
+ * objective terms sum_i <R_i, T_i> (p1 / 2) and sum_i <D_i, T_i> (p2)
  *     reference: ALMCalq12p12 -> LORADSObjConstrValAll -> LORADSUVt/objAUV/coneAUV, lorads_alm.c:714-734,
- *     lorads_alg_common.c:43-90,153-176 ; mul_rk, lorads_sdp_data.c:750-763 */
-template <int G, bool EPI>
-__global__ void __launch_bounds__(LGPU_TPB) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
-                                                      const int32_t *__restrict__ fcol, const double *__restrict__ fval,
-                                                      const double *__restrict__ X, const double *__restrict__ Xl, int ld,
-                                                      double *__restrict__ T,
-                                                      const double *__restrict__ Rm, const int32_t *__restrict__ rcptr,
-                                                      const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
-                                                      double *__restrict__ q1, double *__restrict__ q2, double *partials,
-                                                      unsigned int *counter, double *dsc, SlotSpec<2> spec)
+ *     lorads_alg_common.c:43-90,153-176 */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_epi(int64_t n, int ld, const double *__restrict__ Rm,
+                                                     const double *__restrict__ D, const double *__restrict__ T,
+                                                     const int32_t *__restrict__ rcptr, const int32_t *__restrict__ rcgid,
+                                                     const double *__restrict__ rca, double *__restrict__ q1,
+                                                     double *__restrict__ q2, double *partials, unsigned int *counter,
+                                                     double *dsc, SlotSpec<2> spec)
 {
     const int lane = threadIdx.x % G;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -488,54 +526,91 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_spmm(int64_t n, const int32_t *
         const int64_t i = g0 + it * groups;
         const bool live = i < n;
         double rd = 0.0, dd = 0.0;
-        if (live) {
-            const int e0 = fptr[i], e1 = fptr[i + 1];
-            for (int cb = 0; cb < ld2; cb += G) {
-                const int c = cb + lane;
-                if (c < ld2) {
-                    double2 acc = make_double2(0.0, 0.0);
-                    int e = e0;
-                    for (; e + 3 < e1; e += 4) {
-                        const int c0 = fcol[e], c1 = fcol[e + 1], c2 = fcol[e + 2], c3 = fcol[e + 3];
-                        const double s0 = fval[e], s1 = fval[e + 1], s2 = fval[e + 2], s3 = fval[e + 3];
-                        const double2 x0 = reinterpret_cast<const double2 *>(X + (size_t)c0 * ld)[c];
-                        const double2 x1 = reinterpret_cast<const double2 *>(X + (size_t)c1 * ld)[c];
-                        const double2 x2 = reinterpret_cast<const double2 *>(X + (size_t)c2 * ld)[c];
-                        const double2 x3 = reinterpret_cast<const double2 *>(X + (size_t)c3 * ld)[c];
-                        acc.x = fma(s0, x0.x, acc.x); acc.y = fma(s0, x0.y, acc.y);
-                        acc.x = fma(s1, x1.x, acc.x); acc.y = fma(s1, x1.y, acc.y);
-                        acc.x = fma(s2, x2.x, acc.x); acc.y = fma(s2, x2.y, acc.y);
-                        acc.x = fma(s3, x3.x, acc.x); acc.y = fma(s3, x3.y, acc.y);
-                    }
-                    for (; e < e1; ++e) {
-                        const double s0 = fval[e];
-                        const double2 x0 = reinterpret_cast<const double2 *>(X + (size_t)fcol[e] * ld)[c];
-                        acc.x = fma(s0, x0.x, acc.x); acc.y = fma(s0, x0.y, acc.y);
-                    }
-                    reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
-                    if (EPI) {
-                        const double2 r = reinterpret_cast<const double2 *>(Rm + (size_t)i * ld)[c];
-                        const double2 d = reinterpret_cast<const double2 *>(Xl + (size_t)i * ld)[c];
-                        rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
-                        dd = fma(d.x, d.x, dd); dd = fma(d.y, d.y, dd);
-                        red[0] = fma(r.x, acc.x, red[0]); red[0] = fma(r.y, acc.y, red[0]);
-                        red[1] = fma(d.x, acc.x, red[1]); red[1] = fma(d.y, acc.y, red[1]);
-                    }
-                }
+        if (live)
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                const double2 r = reinterpret_cast<const double2 *>(Rm)[w];
+                const double2 d = reinterpret_cast<const double2 *>(D)[w];
+                const double2 t = reinterpret_cast<const double2 *>(T)[w];
+                rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
+                dd = fma(d.x, d.x, dd); dd = fma(d.y, d.y, dd);
+                red[0] = fma(r.x, t.x, red[0]); red[0] = fma(r.y, t.y, red[0]);
+                red[1] = fma(d.x, t.x, red[1]); red[1] = fma(d.y, t.y, red[1]);
             }
-        }
-        if (EPI) {
-            rd = group_sum<G>(rd);
-            dd = group_sum<G>(dd);
-            if (live && lane == 0)
-                for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) {
-                    const double a = rca[t];
-                    q1[rcgid[t]] = 2.0 * (a * rd);
-                    q2[rcgid[t]] = a * dd;
-                }
-        }
+        rd = group_sum<G>(rd);
+        dd = group_sum<G>(dd);
+        if (live && lane == 0)
+            for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) {
+                const double a = rca[t];
+                q1[rcgid[t]] = 2.0 * (a * rd);
+                q2[rcgid[t]] = a * dd;
+            }
     }
-    if (EPI) grid_reduce_finish<2>(red, partials, counter, dsc, spec);
+    grid_reduce_finish<2>(red, partials, counter, dsc, spec);
+}
+
+/* L-BFGS direction from precomputed coefficients (history length 2), one pass, with the constraint-operator
+ * epilogue:  q = G ; q -= a1 y1 ; [q -= a0 y0 ; q += w0 s0 ;] q += w1 s1 ; D = -q   -- the reference's axpy sequence
+ * (lorads_alm.c:468-505) with alpha / beta scalars obtained from carried inner products instead of four extra
+ * passes.  nn = 0: D = -G.  Also q1_k = 2 a_k <R_i, D_i>, q2_k = a_k <D_i, D_i> and sum_i <(C R)_i, D_i> = <C, R D^T>. */
+struct DirCoef {
+    double a1, a0, w0, w1;
+    int nn;
+};
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirCoef cf, const double *__restrict__ Gd,
+                                                         const double *__restrict__ s1, const double *__restrict__ y1,
+                                                         const double *__restrict__ s0, const double *__restrict__ y0,
+                                                         const double *__restrict__ Rm, const double *__restrict__ CR,
+                                                         double *__restrict__ D, const int32_t *__restrict__ rcptr,
+                                                         const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
+                                                         double *__restrict__ q1, double *__restrict__ q2, double *partials,
+                                                         unsigned int *counter, double *dsc, SlotSpec<1> spec)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (n + groups - 1) / groups;
+    double red[1] = {0.0};
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        double rd = 0.0, dd = 0.0;
+        if (live)
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                double2 q = reinterpret_cast<const double2 *>(Gd)[w];
+                if (cf.nn >= 1) {
+                    const double2 yb = reinterpret_cast<const double2 *>(y1)[w];
+                    q.x = fma(-cf.a1, yb.x, q.x); q.y = fma(-cf.a1, yb.y, q.y);
+                    if (cf.nn >= 2) {
+                        const double2 ya = reinterpret_cast<const double2 *>(y0)[w];
+                        const double2 sa = reinterpret_cast<const double2 *>(s0)[w];
+                        q.x = fma(-cf.a0, ya.x, q.x); q.y = fma(-cf.a0, ya.y, q.y);
+                        q.x = fma(cf.w0, sa.x, q.x); q.y = fma(cf.w0, sa.y, q.y);
+                    }
+                    const double2 sb = reinterpret_cast<const double2 *>(s1)[w];
+                    q.x = fma(cf.w1, sb.x, q.x); q.y = fma(cf.w1, sb.y, q.y);
+                }
+                const double2 d = make_double2(-q.x, -q.y);
+                reinterpret_cast<double2 *>(D)[w] = d;
+                const double2 r = reinterpret_cast<const double2 *>(Rm)[w];
+                const double2 cr = reinterpret_cast<const double2 *>(CR)[w];
+                rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
+                dd = fma(d.x, d.x, dd); dd = fma(d.y, d.y, dd);
+                red[0] = fma(cr.x, d.x, red[0]); red[0] = fma(cr.y, d.y, red[0]);
+            }
+        rd = group_sum<G>(rd);
+        dd = group_sum<G>(dd);
+        if (live && lane == 0)
+            for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) {
+                const double a = rca[t];
+                q1[rcgid[t]] = 2.0 * (a * rd);
+                q2[rcgid[t]] = a * dd;
+            }
+    }
+    grid_reduce_finish<1>(red, partials, counter, dsc, spec);
 }
 
 /* One fused streaming pass for everything that follows the line search (tau known):
@@ -545,7 +620,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_spmm(int64_t n, const int32_t *
  *   updateDimacsALM: constrValSum <- A(R R^T) from scratch, |b - A|^2      lorads_alg_common.c:386-394,424-428
  * C R is carried as CR <- CR + tau (C D) with C D = T from k_mc_spmm.
  * reductions: [0] sum Grad^2, [1] <y,s>, [2] sum (b - A(RR^T))^2 */
-template <int G>
+template <int G, bool GRAM>
 __global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double tau, double rho, double *__restrict__ Rm,
                                                       const double *__restrict__ D, double *__restrict__ CR,
                                                       const double *__restrict__ T, double *__restrict__ Gd,
@@ -554,16 +629,23 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double 
                                                       const double *__restrict__ rca, const double *__restrict__ lam,
                                                       const double *__restrict__ b, double *__restrict__ cvs,
                                                       const double *__restrict__ q1, const double *__restrict__ q2,
-                                                      double *__restrict__ M1, double *partials, unsigned int *counter,
-                                                      double *dsc, SlotSpec<3> spec, int beta_slot)
+                                                      double *__restrict__ M1, const double *__restrict__ so,
+                                                      const double *__restrict__ yo, double *partials, unsigned int *counter,
+                                                      double *dsc, SlotSpec<GRAM ? 10 : 3> spec, int beta_slot)
 {
+    /* GRAM: also the inner products the next direction needs, with (sn, yn) the pair formed here and (so, yo) the
+     * pair that stays in the history: [3] <g,sn> [4] <g,yn> [5] <g,so> [6] <g,yo> [7] <so,yn> [8] <yo,yn> [9] <yn,yn>
+     * (g = the new gradient) */
+    constexpr int NR = GRAM ? 10 : 3;
     const int lane = threadIdx.x % G;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int ld2 = ld >> 1;
     const int64_t iters = (n + groups - 1) / groups;
     const double t2 = tau * tau;
-    double red[3] = {0.0, 0.0, 0.0};
+    double red[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) red[k] = 0.0;
     for (int64_t it = 0; it < iters; ++it) {
         const int64_t i = g0 + it * groups;
         const bool live = i < n;
@@ -601,6 +683,17 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double 
                 reinterpret_cast<double2 *>(yh)[w] = yv;
                 red[0] = fma(gn.x, gn.x, red[0]); red[0] = fma(gn.y, gn.y, red[0]);
                 red[1] = fma(yv.x, sv.x, red[1]); red[1] = fma(yv.y, sv.y, red[1]);
+                if (GRAM) {
+                    const double2 os = reinterpret_cast<const double2 *>(so)[w];
+                    const double2 oy = reinterpret_cast<const double2 *>(yo)[w];
+                    red[3] = fma(gn.x, sv.x, red[3]); red[3] = fma(gn.y, sv.y, red[3]);
+                    red[4] = fma(gn.x, yv.x, red[4]); red[4] = fma(gn.y, yv.y, red[4]);
+                    red[5] = fma(gn.x, os.x, red[5]); red[5] = fma(gn.y, os.y, red[5]);
+                    red[6] = fma(gn.x, oy.x, red[6]); red[6] = fma(gn.y, oy.y, red[6]);
+                    red[7] = fma(os.x, yv.x, red[7]); red[7] = fma(os.y, yv.y, red[7]);
+                    red[8] = fma(oy.x, yv.x, red[8]); red[8] = fma(oy.y, yv.y, red[8]);
+                    red[9] = fma(yv.x, yv.x, red[9]); red[9] = fma(yv.y, yv.y, red[9]);
+                }
                 rr = fma(r.x, r.x, rr); rr = fma(r.y, r.y, rr);
             }
         }
@@ -615,8 +708,8 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double 
             }
     }
     const int ys_slot = spec.slot[1];
-    grid_reduce_finish<3>(red, partials, counter, dsc, spec,
-                          [=] __device__(double *sc) { sc[beta_slot] = 1.0 / sc[ys_slot]; });
+    grid_reduce_finish<NR>(red, partials, counter, dsc, spec,
+                           [=] __device__(double *sc) { sc[beta_slot] = 1.0 / sc[ys_slot]; });
 }
 
 /* Grad = 2 (CR + Diag(sum_k M1_k a_k) R) and sum Grad^2, with CR = C R already formed    lorads_alm.c:32-87 */

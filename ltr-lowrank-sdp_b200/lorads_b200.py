@@ -111,6 +111,7 @@ def lib() -> ctypes.CDLL:
         "lgpu_alm_inner_update": (i, [_vp, d, d, _c_dp, _c_dp]),
         "lgpu_set_fused_path": (i, [_vp, i]),
         "lgpu_uses_fused_path": (i, [_vp]),
+        "lgpu_set_carried_dots": (i, [_vp, i]),
         "lgpu_lbfgs_push": (i, [_vp, d]),
         "lgpu_primal_infeasibility": (i, [_vp, i, _c_dp]),
         "lgpu_update_dual_var": (i, [_vp, d]),
@@ -413,6 +414,9 @@ class Context:
 
     def set_fused_path(self, on: bool):
         self._ck(self._L.lgpu_set_fused_path(self._h, 1 if on else 0), "lgpu_set_fused_path")
+
+    def set_carried_dots(self, on: bool):
+        self._ck(self._L.lgpu_set_carried_dots(self._h, 1 if on else 0), "lgpu_set_carried_dots")
 
     @property
     def uses_fused_path(self) -> bool:

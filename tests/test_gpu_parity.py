@@ -100,7 +100,7 @@ def _load_vars(ctx, g, nc, nlp):
 MAXCUT = ("G11", "maxcut_torus_8x10", "maxcut_torus_20x30")
 
 
-@pytest.mark.parametrize("mode", ["split_calls", "inner_update", "general_path"])
+@pytest.mark.parametrize("mode", ["split_calls", "inner_update", "general_path", "sequential_dots"])
 @pytest.mark.parametrize("name", FIXTURES)
 def test_alm_admm_sequence_vs_reference(lb, name, mode):
     """The exact call sequence oracle/make_golden.py drove through the reference: gradient, five ALM inner
@@ -108,10 +108,13 @@ def test_alm_admm_sequence_vs_reference(lb, name, mode):
     ADMM objective / infeasibility, rank augmentation."""
     g, p, ctx, q, cones = _problem(lb, name)
     nc, nlp = len(cones), q.nlp
-    if mode == "general_path":
+    if mode in ("general_path", "sequential_dots"):
         if name not in MAXCUT:
             pytest.skip("only MaxCut-type problems have a fused path to switch off")
-        ctx.set_fused_path(False)
+        if mode == "general_path":
+            ctx.set_fused_path(False)
+        else:
+            ctx.set_carried_dots(False)
     _load_vars(ctx, g, nc, nlp)
     assert ctx.uses_fused_path == (name in MAXCUT and mode != "general_path")
     for c in range(nc):  # host <-> device layout round trip is exact
@@ -133,7 +136,7 @@ def test_alm_admm_sequence_vs_reference(lb, name, mode):
             assert rel(ctx.get_vec(lb.VEC_ARD), g["q1_first"]) < KTOL
             assert rel(ctx.get_vec(lb.VEC_ADD), g["q2_first"]) < KTOL
         nroot, tau = _line_search(lb, rho, terms)
-        if mode == "inner_update":
+        if mode in ("inner_update", "sequential_dots"):
             lag, pinf = ctx.alm_inner_update(rho, tau)
         else:
             ctx.alm_step(tau)
@@ -269,11 +272,13 @@ def test_fused_path_tracks_general_path_at_c3_scale(lb):
     R0 = rng.random((n, r)) - rng.random((n, r))
     rho = 1.0 / np.sqrt(n)
     res = {}
-    for fused in (True, False):
+    for fused in (True, False, "sequential_dots"):
         ctx = lb.Context(0).load(p)
-        ctx.set_fused_path(fused)
+        ctx.set_fused_path(bool(fused))
+        if fused == "sequential_dots":
+            ctx.set_carried_dots(False)
         ctx.alloc_vars([r], 2)
-        assert ctx.uses_fused_path == fused
+        assert ctx.uses_fused_path == bool(fused)
         ctx.set_factor(lb.R, 0, R0)
         ctx.init_constr_val(lb.PAIR_RR)
         ctx.alm_cal_grad(rho)
@@ -297,13 +302,17 @@ def test_fused_path_tracks_general_path_at_c3_scale(lb):
         launches = ctx.launch_count
         res[fused] = (np.array(taus), obj, lag2, Rf, Gf, cg, Uf, objA, launches)
         ctx.close()
-    a, b = res[True], res[False]
+    for variant in (True, "sequential_dots"):
+        _compare_paths(res[variant], res[False])
+    assert res[True][8] < res["sequential_dots"][8] < res[False][8]  # launches: carried dots < fused < general
+
+
+def _compare_paths(a, b):
     assert np.all(np.abs(a[0] - b[0]) <= 1e-8 * np.maximum(np.abs(b[0]), 1e-30)), np.max(np.abs(a[0] - b[0]) / np.abs(b[0]))
     assert abs(a[1] - b[1]) <= 1e-10 * abs(b[1]) and abs(a[2] - b[2]) <= 1e-8 * abs(b[2])
     assert rel(a[3], b[3]) < 1e-9 and rel(a[4], b[4]) < 1e-8
     assert abs(a[5] - b[5]) <= max(2, 0.05 * b[5])
     assert rel(a[6], b[6]) < 1e-6 and abs(a[7] - b[7]) <= 1e-8 * abs(b[7])
-    assert a[8] < b[8]  # and it is the cheaper path
 
 
 # ---- end to end: the drop-in binary next to the reference binary -----------------------------------------
