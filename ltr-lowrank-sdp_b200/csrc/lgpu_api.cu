@@ -412,6 +412,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     }
     lgpu_ctx *ctx = new lgpu_ctx();
     ctx->device = device;
+    if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1775,15 +1776,24 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
         for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
         sp.accumulate = 0;
         Prof pr(ctx, KC_MC_STEP);
-        DISPATCH_G(G, k_mc_step<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
-                          c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid,
-                          c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo], ctx->partials,
-                          ctx->counter, ctx->dsc, sp, SC_BETA0 + jn));
+#define MC_STEP(MB)                                                                                                             \
+    DISPATCH_G(G, k_mc_step<GG, true, MB><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, true, MB>), LGPU_TPB, 0,         \
+                                            ctx->stream>>>(c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,    \
+                                                           ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, \
+                                                           ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo],          \
+                                                           ctx->partials, ctx->counter, ctx->dsc, sp, SC_BETA0 + jn))
+        switch (ctx->step_variant) {
+        case 1: MC_STEP(3); break;
+        case 2: MC_STEP(4); break;
+        case 3: MC_STEP(5); break;
+        default: MC_STEP(2); break;
+        }
+#undef MC_STEP
     } else {
         SlotSpec<3> sp;
         sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
         Prof pr(ctx, KC_MC_STEP);
-        DISPATCH_G(G, k_mc_step<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
+        DISPATCH_G(G, k_mc_step<GG, false, 4><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, false, 4>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid,
                           c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials,
                           ctx->counter, ctx->dsc, sp, SC_BETA0 + jn));

@@ -177,6 +177,7 @@ struct lgpu_ctx {
     bool cr_valid = false, cd_valid = false;
     int cr_updates = 0;
     /* carried inner products of the two L-BFGS pairs and the current gradient (fused path, history length 2) */
+    int step_variant = 1; /* min CTAs/SM of k_mc_step: 0 -> 2, 1 -> 3 (default; measured best: 80 registers, no spills), 2 -> 4, 3 -> 5 */
     bool gram_enabled = true;
     bool gram_valid = false;
     bool gram_pair_ok[2] = {false, false};

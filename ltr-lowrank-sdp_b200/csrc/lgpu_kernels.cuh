@@ -620,8 +620,8 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
  *   updateDimacsALM: constrValSum <- A(R R^T) from scratch, |b - A|^2      lorads_alg_common.c:386-394,424-428
  * C R is carried as CR <- CR + tau (C D) with C D = T from k_mc_spmm.
  * reductions: [0] sum Grad^2, [1] <y,s>, [2] sum (b - A(RR^T))^2 */
-template <int G, bool GRAM>
-__global__ void __launch_bounds__(LGPU_TPB) k_mc_step(int64_t n, int ld, double tau, double rho, double *__restrict__ Rm,
+template <int G, bool GRAM, int MINB>
+__global__ void __launch_bounds__(LGPU_TPB, MINB) k_mc_step(int64_t n, int ld, double tau, double rho, double *__restrict__ Rm,
                                                       const double *__restrict__ D, double *__restrict__ CR,
                                                       const double *__restrict__ T, double *__restrict__ Gd,
                                                       double *__restrict__ sh, double *__restrict__ yh,

@@ -353,8 +353,10 @@ class Context:
         assert a.shape == (self.dims[c], self.rank[c]), (a.shape, self.dims[c], self.rank[c])
         self._ck(self._L.lgpu_set_factor(self._h, which, c, _dp(a)), "lgpu_set_factor")
 
-    def get_factor(self, which: int, c: int) -> np.ndarray:
-        a = np.zeros((self.dims[c], self.rank[c]), order="F")
+    def get_factor(self, which: int, c: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`out`: optional Fortran-ordered (n, r) destination, e.g. a view of pinned memory"""
+        a = np.zeros((self.dims[c], self.rank[c]), order="F") if out is None else out
+        assert a.shape == (self.dims[c], self.rank[c]) and a.flags.f_contiguous and a.dtype == np.float64
         self._ck(self._L.lgpu_get_factor(self._h, which, c, _dp(a)), "lgpu_get_factor")
         return a
 
@@ -372,8 +374,9 @@ class Context:
         assert v.shape == (self.m,)
         self._ck(self._L.lgpu_set_vec(self._h, which, _dp(v)), "lgpu_set_vec")
 
-    def get_vec(self, which: int) -> np.ndarray:
-        v = np.zeros(self.m)
+    def get_vec(self, which: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        v = np.zeros(self.m) if out is None else out
+        assert v.shape == (self.m,) and v.flags.c_contiguous and v.dtype == np.float64
         self._ck(self._L.lgpu_get_vec(self._h, which, _dp(v)), "lgpu_get_vec")
         return v
 
