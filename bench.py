@@ -397,8 +397,9 @@ def run_ours(args):
         t = torch.tensor([e2e_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
-    h2d = (8.0 * n * r + 8.0 * n) / args.steps
-    d2h = (8.0 * n * r + 16.0 * n) / args.steps + 9 * 8
+    # whole-job bytes: each rank moves only its rows of the factor; the m-vectors go to / come from every rank
+    h2d = (8.0 * n * r + world * 8.0 * n) / args.steps
+    d2h = (8.0 * n * r + world * 16.0 * n) / args.steps + world * 17 * 8
     assert np.isfinite(Rfin[::997]).all() and np.isfinite(out[2])
     e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": "initial factor host->device, K iterations via the C ABI with the line search on the host, final "

@@ -101,6 +101,11 @@ int lgpu_uses_fused_path(const lgpu_ctx *ctx);
  * costs one pass.  Same operations on the same numbers up to the rounding of those inner products.  Switch
  * (default 1) for A/B parity tests. */
 int lgpu_set_carried_dots(lgpu_ctx *ctx, int on);
+/* Cones whose aggregate is dense (the reference's SDP_COEFF_DENSE aggregate: n < 20, a dense member, or >= 10 % fill,
+ * lorads_sdp_conic.c:1185-1393) run LORADSUVt's dsyr2k and mul_rk's dsymm (lorads_alg_common.c:72-89,
+ * lorads_sdp_data.c:948-973) as DMMA (FP64 tensor core) kernels over the packed triangle.  Switch (default 1) for A/B
+ * tests against the pattern-gather kernels. */
+int lgpu_set_dense_tensor_path(lgpu_ctx *ctx, int on);
 int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double *colmajor);
 int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *colmajor);
 int lgpu_set_lp(lgpu_ctx *ctx, int which, const double *v);
@@ -178,7 +183,9 @@ int lgpu_op_wsum_mulrk(lgpu_ctx *ctx, int cone, int64_t r, const double *w, int 
  * of the scalar packs (L-BFGS dots, the seven line-search terms, |Grad|^2 / <y,s> / |b - A|^2, CG dots).  This build
  * partitions the fused MaxCut-type layout (one SDP block, single-diagonal-entry constraints).
  * Order of calls: lgpu_create, lgpu_comm_init, lgpu_set_problem, lgpu_cone_upload (every rank passes the WHOLE
- * problem and keeps its slice), lgpu_alloc_vars, ... ; host factors/vectors passed in or out are always whole. */
+ * problem and keeps its slice), lgpu_alloc_vars, ... ; host factors/vectors passed IN are always whole (a rank reads
+ * only its rows from them); lgpu_get_factor writes only the rows the rank owns into the caller's whole-size array;
+ * lgpu_get_vec returns the whole m-vector on every rank. */
 int lgpu_partition_rows(int64_t n, int world, int rank, int64_t *lo, int64_t *hi, int64_t *rows_per_rank);
 /* ncclUniqueId is 128 bytes; rank 0 calls lgpu_nccl_unique_id and the host side distributes it to the other ranks */
 int lgpu_nccl_unique_id(unsigned char id[128]);

@@ -337,8 +337,18 @@ static inline int pick_list_group(double avg_len)
 /* UVt on the pattern of cone c from two row-major factors */
 static void run_uvt(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *U, const double *V, double *out)
 {
-    const int G = pick_group(ld);
     const int same = (U == V) ? 1 : 0;
+    if (c.dense_aggregate && ctx->dense_dmma) {
+        /* the pattern is the whole triangle: (U V^T + V U^T)/2 as a rank-2k update on the FP64 tensor pipe */
+        const int64_t nt = (c.n + 15) / 16, ntiles = nt * (nt + 1) / 2;
+        int64_t blocks = (ntiles + 3) / 4;
+        const int64_t cap = (int64_t)ctx->num_sms * 8;
+        if (blocks > cap) blocks = cap;
+        Prof pr(ctx, KC_DENSE);
+        k_dense_uvt<<<(unsigned)blocks, 128, 0, ctx->stream>>>(c.n, (int)ld, U, V, same, out);
+        return;
+    }
+    const int G = pick_group(ld);
     Prof pr(ctx, KC_UVT);
     DISPATCH_G(G, k_uvt<GG><<<grid_for(ctx, c.nnzP * GG, (const void *)k_uvt<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.nnzP, c.pat_row, c.pat_col, U, V, (int)ld, same, out));
@@ -373,6 +383,15 @@ static void run_wsum(lgpu_ctx *ctx, DevCone &c, const double *w, bool w_global, 
 static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, const double *X, double alpha, double beta,
                      const double *Z, double *Y)
 {
+    if (c.dense_aggregate && ctx->dense_dmma) {
+        const int64_t ntiles = ((c.n + 7) / 8) * ((ld + 63) / 64);
+        int64_t blocks = (ntiles + 3) / 4;
+        const int64_t cap = (int64_t)ctx->num_sms * 8;
+        if (blocks > cap) blocks = cap;
+        Prof pr(ctx, KC_DENSE);
+        k_dense_symm<<<(unsigned)blocks, 128, 0, ctx->stream>>>(c.n, (int)ld, S, X, alpha, beta, Z, Y);
+        return;
+    }
     const int G = pick_group(ld);
     Prof pr(ctx, KC_SPMM);
     DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG, (const void *)k_spmm<GG>), LGPU_TPB, 0, ctx->stream>>>(
@@ -481,7 +500,7 @@ extern "C" int lgpu_profile_num_classes(void) { return KC_COUNT; }
 extern "C" const char *lgpu_profile_class_name(int cls)
 {
     static const char *names[KC_COUNT] = {"k_uvt", "k_gather", "k_wsum", "k_spmm", "k_vec", "k_reduce", "k_scalar",
-                                          "k_layout", "k_mc_spmm", "k_mc_step", "k_mc_dir"};
+                                          "k_layout", "k_mc_spmm", "k_mc_step", "k_mc_dir", "k_dense_dmma"};
     return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
 }
 
@@ -1090,6 +1109,13 @@ extern "C" int lgpu_set_fused_path(lgpu_ctx *ctx, int on)
     return 0;
 }
 extern "C" int lgpu_uses_fused_path(const lgpu_ctx *ctx) { return (ctx && ctx->mc) ? 1 : 0; }
+/* A/B switch: dense-aggregate cones on the FP64 tensor pipe (default on) vs the pattern-gather kernels */
+extern "C" int lgpu_set_dense_tensor_path(lgpu_ctx *ctx, int on)
+{
+    if (!ctx) return 1;
+    ctx->dense_dmma = on != 0;
+    return 0;
+}
 /* A/B switch: carried inner products for the L-BFGS scalars (default on) vs the two-loop recursion's own passes */
 extern "C" int lgpu_set_carried_dots(lgpu_ctx *ctx, int on)
 {
@@ -1137,43 +1163,50 @@ static double *mvec_of(lgpu_ctx *ctx, int which)
 }
 
 /* host column-major n x r -> device row-major n x ld at dst */
-/* host column-major n_glob x r -> device row-major rows [row_lo, row_lo + n) x ld at dst */
+/* host column-major n_glob x r -> device row-major rows [row_lo, row_lo + n) x ld at dst.  Only the owned rows cross
+ * the bus (a strided 2-D copy: r column pieces of n doubles). */
 static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *cm, double *dst, int64_t n_glob = -1,
                          int64_t row_lo = 0)
 {
     if (n_glob < 0) n_glob = n;
-    const size_t bytes = sizeof(double) * (size_t)n_glob * (size_t)r;
+    if (n <= 0) return 0;
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
     /* straight from the caller's buffer: a pinned buffer goes by DMA, a pageable one is staged by the runtime */
     TRY(ensure_dstage(ctx, bytes));
-    CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_glob == n)
+        CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CU(ctx, cudaMemcpy2DAsync(ctx->dstage, sizeof(double) * (size_t)n, cm + row_lo, sizeof(double) * (size_t)n_glob,
+                                  sizeof(double) * (size_t)n, (size_t)r, cudaMemcpyHostToDevice, ctx->stream));
     dim3 blk(32, 8);
-    if (n > 0) {
+    {
         Prof pr(ctx, KC_LAYOUT);
-        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, n_glob, row_lo, dst);
+        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, n, 0, dst);
     }
     CHECK_LAUNCH(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); /* the caller may reuse its buffer as soon as this returns */
     return 0;
 }
-/* the reverse; in a partitioned run every rank writes its rows into a zeroed full-size staging array and the
- * arrays are summed over the ranks, so every rank returns the complete factor */
+/* the reverse.  In a partitioned run each rank writes ONLY the rows it owns into the caller's n_glob x r array (the
+ * other rows are left untouched); the caller assembles the ranks' pieces if it needs the whole factor. */
 static int download_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *src, double *cm, int64_t n_glob = -1,
                            int64_t row_lo = 0)
 {
     if (n_glob < 0) n_glob = n;
-    const size_t bytes = sizeof(double) * (size_t)n_glob * (size_t)r;
+    if (n <= 0) return 0;
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
     TRY(ensure_dstage(ctx, bytes));
-    if (ctx->world > 1) CU(ctx, cudaMemsetAsync(ctx->dstage, 0, bytes, ctx->stream));
     dim3 blk(32, 8);
-    if (n > 0) {
+    {
         Prof pr(ctx, KC_LAYOUT);
-        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage, n_glob, row_lo);
+        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage, n, 0);
     }
     CHECK_LAUNCH(ctx);
-    if (ctx->world > 1)
-        NC(ctx, g_nccl.AllReduce(ctx->dstage, ctx->dstage, (size_t)n_glob * (size_t)r, LG_NCCL_FLOAT64, LG_NCCL_SUM,
-                                 (lg_ncclComm_t)ctx->comm, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(cm, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_glob == n)
+        CU(ctx, cudaMemcpyAsync(cm, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+        CU(ctx, cudaMemcpy2DAsync(cm + row_lo, sizeof(double) * (size_t)n_glob, ctx->dstage, sizeof(double) * (size_t)n,
+                                  sizeof(double) * (size_t)n, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

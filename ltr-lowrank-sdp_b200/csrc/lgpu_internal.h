@@ -76,6 +76,7 @@ enum {
     KC_MC_SPMM,     /* MaxCut-type fused: T = C D with q1/q2/p1/p2 epilogue */
     KC_MC_STEP,     /* MaxCut-type fused: step + gradient + L-BFGS pair + A(RR^T) */
     KC_MC_DIR,      /* fused two-loop passes */
+    KC_DENSE,       /* dense-aggregate cones: DMMA SYR2K / SYMM */
     KC_COUNT
 };
 
@@ -171,6 +172,7 @@ struct lgpu_ctx {
     void *comm = nullptr;     /* ncclComm_t */
     double *gfull = nullptr;  /* [world * n_alloc * ld] all-gathered factor rows for the sparse product */
     /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */
+    bool dense_dmma = true;   /* dense-aggregate cones: SYR2K / SYMM on the FP64 tensor pipe */
     bool fast_enabled = true;
     bool mc = false;
     double *CR = nullptr, *CD = nullptr;

@@ -184,6 +184,118 @@ __global__ void __launch_bounds__(LGPU_TPB) k_uvt(int64_t nnzP, const int32_t *_
     }
 }
 
+/* ================================================================================================
+ * Dense-aggregate cones (theta / matrix-completion type: the pattern is the whole lower triangle, slot = packed
+ * column-major index).  Here the two heavy operators ARE matrix products, so they run on the FP64 tensor pipe:
+ * DMMA m8n8k4 (mma.sync ... f64), fragments straight from the row-major factors.
+ * fragment layout (PTX ISA, m8n8k4 .f64): g = lane >> 2, t = lane & 3
+ *   A (8x4, row):  a  = A[g][t]          B (4x8, col):  b = B[t][g]          C (8x8):  c0 = C[g][2t], c1 = C[g][2t+1]
+ * ================================================================================================*/
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+/* K1d  W = (U V^T + V U^T)/2 on the packed lower triangle         reference: LORADSUVt dense branch -> fds_syr2k
+ *      (dsyr2k, alpha = 1/2), lorads_alg_common.c:72-89, lorads_dense_opts.c:773-783
+ * One warp per 16 x 16 tile (I >= J) of W, 2 x 2 DMMA tiles, k in steps of 4 over the padded rank. */
+__global__ void __launch_bounds__(128) k_dense_uvt(int64_t n, int ld, const double *__restrict__ U,
+                                                   const double *__restrict__ V, int same, double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int64_t nt = (n + 15) / 16;
+    const int64_t ntiles = nt * (nt + 1) / 2;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < ntiles; w += warps) {
+        /* w -> (I, J), I >= J, tiles of row I start at I (I + 1) / 2 */
+        int64_t I = (int64_t)((sqrt(8.0 * (double)w + 1.0) - 1.0) * 0.5);
+        while (I * (I + 1) / 2 > w) --I;
+        while ((I + 1) * (I + 2) / 2 <= w) ++I;
+        const int64_t J = w - I * (I + 1) / 2;
+        const int64_t i0 = I * 16, j0 = J * 16;
+        double c[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+        for (int k0 = 0; k0 < ld; k0 += 4) {
+            double ui[2], vi[2], uj[2], vj[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int64_t ri = i0 + a * 8 + g, rj = j0 + a * 8 + g;
+                ui[a] = ri < n ? U[(size_t)ri * ld + k0 + t] : 0.0;
+                uj[a] = rj < n ? U[(size_t)rj * ld + k0 + t] : 0.0;
+                vi[a] = same ? ui[a] : (ri < n ? V[(size_t)ri * ld + k0 + t] : 0.0);
+                vj[a] = same ? uj[a] : (rj < n ? V[(size_t)rj * ld + k0 + t] : 0.0);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    dmma_m8n8k4(c[a][b][0], c[a][b][1], ui[a], vj[b]); /* U_i V_j^T */
+                    dmma_m8n8k4(c[a][b][0], c[a][b][1], vi[a], uj[b]); /* V_i U_j^T */
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int64_t i = i0 + a * 8 + g, j = j0 + b * 8 + 2 * t + e;
+                    if (i < n && j <= i) out[(2 * n - j - 1) * j / 2 + i] = 0.5 * c[a][b][e];
+                }
+    }
+}
+
+/* K4d  Y = alpha S X + beta Z, S dense symmetric given on the packed lower triangle (never unpacked to n x n)
+ *      reference: dataMatDenseMultiRkMat (unpack + dsymm on every call), lorads_sdp_data.c:948-973
+ * One warp per 8 rows x 64 columns of Y; the S fragment of a k-step is reused by the 8 column tiles. */
+__global__ void __launch_bounds__(128) k_dense_symm(int64_t n, int ld, const double *__restrict__ S,
+                                                    const double *__restrict__ X, double alpha, double beta,
+                                                    const double *__restrict__ Z, double *__restrict__ Y)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int64_t rt = (n + 7) / 8;
+    const int ct = (ld + 63) / 64;
+    const int64_t ntiles = rt * ct;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < ntiles; w += warps) {
+        const int64_t i0 = (w / ct) * 8;
+        const int c0 = (int)(w % ct) * 64;
+        const int64_t i = i0 + g;
+        double acc[8][2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
+        for (int64_t k0 = 0; k0 < n; k0 += 4) {
+            const int64_t k = k0 + t;
+            double a = 0.0;
+            if (i < n && k < n) a = (i >= k) ? S[(2 * n - k - 1) * k / 2 + i] : S[(2 * n - i - 1) * i / 2 + k];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = c0 + q * 8 + g;
+                const double b = (k < n && col < ld) ? X[(size_t)k * ld + col] : 0.0;
+                dmma_m8n8k4(acc[q][0], acc[q][1], a, b);
+            }
+        }
+        if (i < n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = c0 + q * 8 + 2 * t + e;
+                    if (col < ld) {
+                        double o = alpha * acc[q][e];
+                        if (Z != nullptr) o = fma(beta, Z[(size_t)i * ld + col], o);
+                        Y[(size_t)i * ld + col] = o;
+                    }
+                }
+        }
+    }
+}
+
 /* diag_only cones, CG operator: only the diagonal samples are ever read (A_i = a e_d e_d^T)
  * cv[t] = a_t * <U_d, V_d>                 reference: sdp*ConeAUVImpl on 1-entry diagonal constraints */
 template <int G>

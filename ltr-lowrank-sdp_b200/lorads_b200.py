@@ -112,6 +112,7 @@ def lib() -> ctypes.CDLL:
         "lgpu_set_fused_path": (i, [_vp, i]),
         "lgpu_uses_fused_path": (i, [_vp]),
         "lgpu_set_carried_dots": (i, [_vp, i]),
+        "lgpu_set_dense_tensor_path": (i, [_vp, i]),
         "lgpu_lbfgs_push": (i, [_vp, d]),
         "lgpu_primal_infeasibility": (i, [_vp, i, _c_dp]),
         "lgpu_update_dual_var": (i, [_vp, d]),
@@ -418,6 +419,9 @@ class Context:
     def set_fused_path(self, on: bool):
         self._ck(self._L.lgpu_set_fused_path(self._h, 1 if on else 0), "lgpu_set_fused_path")
 
+    def set_dense_tensor_path(self, on: bool):
+        self._ck(self._L.lgpu_set_dense_tensor_path(self._h, 1 if on else 0), "lgpu_set_dense_tensor_path")
+
     def set_carried_dots(self, on: bool):
         self._ck(self._L.lgpu_set_carried_dots(self._h, 1 if on else 0), "lgpu_set_carried_dots")
 
@@ -566,24 +570,31 @@ def random_graph(n: int, out_degree: int, seed: int):
 
 
 def write_sdpa(path: str, p: SdpaProblem) -> None:
-    """Write an SdpaProblem back to SDPA sparse text (objective sign restored), SDP blocks only."""
+    """Write an SdpaProblem back to SDPA sparse text (objective sign restored), SDP blocks only.  Vectorised: the
+    C5-sized instances have ~7e7 entries."""
     with open(path, "w") as f:
         f.write(f"{p.m}\n{p.ncones}\n{' '.join(str(int(d)) for d in p.dims)}\n")
         f.write(" ".join(repr(float(x)) for x in p.b) + "\n")
         for k in range(p.ncones):
             n = int(p.dims[k])
             beg = p.mat_beg[k]
-            for c in range(p.m + 1):
-                idx = p.mat_idx[k][beg[c]:beg[c + 1]]
-                val = p.mat_elem[k][beg[c]:beg[c + 1]]
-                if len(idx) == 0:
-                    continue
-                # invert pack_idx
-                j = np.floor(((2 * n + 1) - np.sqrt((2.0 * n + 1) ** 2 - 8.0 * idx)) / 2.0).astype(np.int64)
-                j = np.clip(j, 0, n - 1)
-                j = np.where(j * (2 * n - j + 1) // 2 > idx, j - 1, j)
-                j = np.where((j + 1) * (2 * n - j) // 2 <= idx, j + 1, j)
-                i = idx - j * (2 * n - j + 1) // 2 + j
-                sgn = -1.0 if c == 0 else 1.0
-                lines = [f"{c} {k + 1} {int(a) + 1} {int(b) + 1} {float(sgn * v)!r}\n" for a, b, v in zip(j, i, val)]
-                f.write("".join(lines))
+            idx, val = p.mat_idx[k], p.mat_elem[k]
+            if len(idx) == 0:
+                continue
+            con = np.repeat(np.arange(p.m + 1, dtype=np.int64), np.diff(beg))
+            # invert pack_idx
+            j = np.floor(((2 * n + 1) - np.sqrt((2.0 * n + 1) ** 2 - 8.0 * idx)) / 2.0).astype(np.int64)
+            j = np.clip(j, 0, n - 1)
+            j = np.where(j * (2 * n - j + 1) // 2 > idx, j - 1, j)
+            j = np.where((j + 1) * (2 * n - j) // 2 <= idx, j + 1, j)
+            i = idx - j * (2 * n - j + 1) // 2 + j
+            v = np.where(con == 0, -val, val)
+            chunk = 2_000_000
+            for a in range(0, len(idx), chunk):
+                sl = slice(a, a + chunk)
+                cols = [con[sl].astype(str), np.full(len(con[sl]), str(k + 1)), (j[sl] + 1).astype(str),
+                        (i[sl] + 1).astype(str), np.array([repr(float(x)) for x in v[sl]])]
+                lines = cols[0]
+                for cc in cols[1:]:
+                    lines = np.char.add(np.char.add(lines, " "), cc)
+                f.write("\n".join(lines.tolist()) + "\n")

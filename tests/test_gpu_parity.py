@@ -100,7 +100,10 @@ def _load_vars(ctx, g, nc, nlp):
 MAXCUT = ("G11", "maxcut_torus_8x10", "maxcut_torus_20x30")
 
 
-@pytest.mark.parametrize("mode", ["split_calls", "inner_update", "general_path", "sequential_dots"])
+DENSE = ("theta_n30", "dense_constraint_n24", "multiblock_sdp", "multiblock_lp", "general_sparse_n60")
+
+
+@pytest.mark.parametrize("mode", ["split_calls", "inner_update", "general_path", "sequential_dots", "dense_gather"])
 @pytest.mark.parametrize("name", FIXTURES)
 def test_alm_admm_sequence_vs_reference(lb, name, mode):
     """The exact call sequence oracle/make_golden.py drove through the reference: gradient, five ALM inner
@@ -108,6 +111,10 @@ def test_alm_admm_sequence_vs_reference(lb, name, mode):
     ADMM objective / infeasibility, rank augmentation."""
     g, p, ctx, q, cones = _problem(lb, name)
     nc, nlp = len(cones), q.nlp
+    if mode == "dense_gather":
+        if not any(ctx.cone_info(c)["dense_aggregate"] for c in range(nc)):
+            pytest.skip("no dense-aggregate cone: nothing runs on the tensor path")
+        ctx.set_dense_tensor_path(False)
     if mode in ("general_path", "sequential_dots"):
         if name not in MAXCUT:
             pytest.skip("only MaxCut-type problems have a fused path to switch off")
@@ -259,6 +266,57 @@ def test_adjoint_and_linearity_at_scale(lb, shape):
     Y2 = ctx.op_wsum_mulrk(0, wv, Vm + Wm, True)
     assert rel(Y2, Y0 + Y1 + ctx.op_wsum_mulrk(0, wv, Wm, True)) < 1e-11
     ctx.close()
+
+
+def _theta_problem(lb, n, p_edge, seed):
+    """Lovasz-theta SDP of G(n, p) in the theta102 shape: C dense (-J, negated on read -> all
+    ones... stored as read: C = -F0 with F0 = J), A_1 = I, A_k = E_ij + E_ji per edge, b = (1, 0, ..., 0)."""
+    rng = np.random.default_rng(seed)
+    iu, ju = np.triu_indices(n, 1)
+    keep = rng.random(len(iu)) < p_edge
+    ei, ej = iu[keep], ju[keep]
+    m = 1 + len(ei)
+    tri_i, tri_j = np.tril_indices(n)          # row >= col
+    obj_idx = lb.pack_idx(n, tri_i.astype(np.int64), tri_j.astype(np.int64))
+    o = np.argsort(obj_idx)
+    obj_idx, obj_val = obj_idx[o], -np.ones(len(o))
+    k = np.arange(n, dtype=np.int64)
+    idx = np.concatenate([obj_idx, lb.pack_idx(n, k, k), lb.pack_idx(n, ej.astype(np.int64), ei.astype(np.int64))])
+    val = np.concatenate([obj_val, np.ones(n), np.ones(len(ei))])
+    beg = np.concatenate([[0, len(obj_idx), len(obj_idx) + n], len(obj_idx) + n + 1 + np.arange(len(ei), dtype=np.int64)])
+    b = np.zeros(m)
+    b[0] = 1.0
+    return lb.SdpaProblem(m, [n], b, [beg], [idx], [val])
+
+
+@pytest.mark.parametrize("n,r", [(96, 16), (203, 22), (333, 40)])
+def test_dense_cone_tensor_path(lb, tmp_path, n, r):
+    """Dense-aggregate cone (theta-type, C dense): LORADSUVt's dsyr2k and mul_rk's dsymm on the FP64 tensor pipe against
+    the numpy oracle and against the pattern-gather kernels; sizes that are not multiples of the DMMA tile."""
+    p = _theta_problem(lb, n, 0.2, n)
+    f = tmp_path / "theta.dat-s"
+    lb.write_sdpa(str(f), p)
+    q = orc.read_sdpa(str(f))
+    cone = orc.build_cone(q.blocks[0], q.m)
+    assert cone.dense_aggregate
+    rng = np.random.default_rng(n)
+    Um, Vm = rng.normal(size=(n, r)), rng.normal(size=(n, r))
+    w = rng.normal(size=q.m)
+    res = {}
+    for tensor in (True, False):
+        ctx = lb.Context(0).load(p)
+        ctx.set_dense_tensor_path(tensor)
+        assert ctx.cone_info(0)["dense_aggregate"]
+        res[tensor] = (ctx.op_uvt(0, Um, Vm), ctx.op_uvt(0, Um, Um), ctx.op_auv(0, Um, Vm), ctx.op_wsum_mulrk(0, w, Vm, True))
+        ctx.close()
+    ot = orc.uvt(cone, Um, Vm)
+    for tensor in (True, False):
+        t_uv, t_uu, (cv, obj), Y = res[tensor]
+        assert rel(t_uv, ot) < KTOL and rel(t_uu, orc.uvt(cone, Um, Um)) < KTOL
+        assert rel(cv, orc.cone_auv(cone, ot)) < KTOL
+        assert abs(obj - orc.obj_auv(cone, ot)) <= KTOL * np.sum(np.abs(ot))
+        assert rel(Y, orc.mul_rk(cone, orc.wsum(cone, w, True), Vm)) < KTOL
+    assert rel(res[True][3], res[False][3]) < KTOL
 
 
 def test_fused_path_tracks_general_path_at_c3_scale(lb):
