@@ -262,7 +262,7 @@ def run_reference(args):
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     r = reference_rate(args, max(args.steps, 1) * 2, args.warmup)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblorads_ref.so is not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/liblorads_ref.so is not built"})
         return
     sample = (f"unmodified reference objects (liblorads_ref.so), same generator/degree/rank at n={r['n_sample']} "
               f"({r['steps']} ALM inner iterations in {r['seconds']:.1f} s = {r['sample_rate']:.3f} it/s), scaled by "
@@ -273,7 +273,7 @@ def run_reference(args):
             "config": config(args, 1),
             "cpu_baseline": {"value": r["scaled"], "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
             "e2e": {"value": r["scaled"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---- our arm -------------------------------------------------------------------------------------------
@@ -429,13 +429,25 @@ def run_ours(args):
             line["time_to_tol"] = time_to_tolerance(lb)
         except Exception as e:  # never lose the headline line to the secondary measurement
             line["time_to_tol"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner, the
+    reference's printf chatter) was sent to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -207,6 +207,10 @@ static struct {
     int (*CommDestroy)(lg_ncclComm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, lg_ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, lg_ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, lg_ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, lg_ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 } g_nccl;
 
@@ -231,7 +235,12 @@ static bool nccl_load(std::string &err)
     *(void **)&g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
     *(void **)&g_nccl.AllGather = dlsym(h, "ncclAllGather");
     *(void **)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather) {
+    *(void **)&g_nccl.Send = dlsym(h, "ncclSend");
+    *(void **)&g_nccl.Recv = dlsym(h, "ncclRecv");
+    *(void **)&g_nccl.GroupStart = dlsym(h, "ncclGroupStart");
+    *(void **)&g_nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.Send ||
+        !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
         err = "libnccl lacks a required symbol";
         return false;
     }
@@ -517,7 +526,7 @@ static void free_vars(lgpu_ctx *ctx)
 {
     dev_free(ctx->R); dev_free(ctx->U); dev_free(ctx->V); dev_free(ctx->G); dev_free(ctx->M2); dev_free(ctx->bLin);
     dev_free(ctx->cg_r); dev_free(ctx->cg_p); dev_free(ctx->cg_Q); dev_free(ctx->stage);
-    dev_free(ctx->CR); dev_free(ctx->CD); dev_free(ctx->gfull);
+    dev_free(ctx->CR); dev_free(ctx->CD); dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
     ctx->cr_valid = ctx->cd_valid = false;
     ctx->mc = false;
     for (auto &p : ctx->s) dev_free(p);
@@ -538,35 +547,16 @@ extern "C" void lgpu_destroy(lgpu_ctx *ctx)
     dev_free(ctx->mtmp);
     dev_free(ctx->lp.obj); dev_free(ctx->lp.r_ptr); dev_free(ctx->lp.r_col); dev_free(ctx->lp.r_val);
     dev_free(ctx->lp.c_ptr); dev_free(ctx->lp.c_row); dev_free(ctx->lp.c_val); dev_free(ctx->lp.nrm2sq);
+    dev_free(ctx->send_idx);
     dev_free(ctx->dsc); dev_free(ctx->partials); dev_free(ctx->counter);
     prof_flush(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((lg_ncclComm_t)ctx->comm);
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     for (auto &e : ctx->timers) if (e) cudaEventDestroy(e);
     if (ctx->hsc) cudaFreeHost(ctx->hsc);
-    if (ctx->hstage) cudaFreeHost(ctx->hstage);
     if (ctx->dstage) cudaFree(ctx->dstage);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
-}
-
-static int ensure_stage(lgpu_ctx *ctx, size_t bytes)
-{
-    if (bytes > ctx->hstage_bytes) {
-        if (ctx->hstage) cudaFreeHost(ctx->hstage);
-        ctx->hstage = nullptr;
-        ctx->hstage_bytes = 0;
-        CU(ctx, cudaMallocHost((void **)&ctx->hstage, bytes));
-        ctx->hstage_bytes = bytes;
-    }
-    if (bytes > ctx->dstage_bytes) {
-        if (ctx->dstage) cudaFree(ctx->dstage);
-        ctx->dstage = nullptr;
-        ctx->dstage_bytes = 0;
-        CU(ctx, cudaMalloc(&ctx->dstage, bytes));
-        ctx->dstage_bytes = bytes;
-    }
-    return 0;
 }
 
 static int ensure_dstage(lgpu_ctx *ctx, size_t bytes)
@@ -837,6 +827,53 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         const int32_t e0 = f_ptr[lo], e1 = f_ptr[hi], k0 = rc_ptr[lo], k1 = rc_ptr[hi];
         std::vector<int32_t> lf_ptr(nl + 1), lf_col(f_col.begin() + e0, f_col.begin() + e1), lrc_ptr(nl + 1),
             lrc_gid(rc_gid.begin() + k0, rc_gid.begin() + k1);
+        /* halo plan.  Every rank holds the whole CSR on the host during upload, so it can derive without any
+         * communication both what it needs from each peer and what each peer needs from it (same lists, same
+         * ascending order on both sides). */
+        const int P = ctx->world;
+        ctx->send_off.assign(P, 0); ctx->send_cnt.assign(P, 0); ctx->recv_off.assign(P, 0); ctx->recv_cnt.assign(P, 0);
+        std::vector<int32_t> remap(n, -1), send_idx;
+        {
+            std::vector<uint8_t> mark(n, 0);
+            for (int32_t e = e0; e < e1; ++e) mark[f_col[e]] = 1;
+            int64_t pos = 0;
+            for (int q = 0; q < P; ++q) {
+                int64_t qlo, qhi, qr;
+                lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
+                ctx->recv_off[q] = pos;
+                if (q != ctx->rank)
+                    for (int64_t j = qlo; j < qhi; ++j)
+                        if (mark[j]) remap[j] = (int32_t)(rpr + pos++);
+                ctx->recv_cnt[q] = pos - ctx->recv_off[q];
+            }
+            ctx->halo_rows = pos;
+            for (int64_t j = lo; j < hi; ++j) remap[j] = (int32_t)(j - lo);
+            std::vector<uint8_t> want(nl);
+            for (int q = 0; q < P; ++q) {
+                ctx->send_off[q] = (int64_t)send_idx.size();
+                if (q == ctx->rank) continue;
+                int64_t qlo, qhi, qr;
+                lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
+                std::fill(want.begin(), want.end(), 0);
+                for (int32_t e = f_ptr[qlo]; e < f_ptr[qhi]; ++e) {
+                    const int32_t j = f_col[e];
+                    if (j >= lo && j < hi) want[j - lo] = 1;
+                }
+                for (int64_t j = 0; j < nl; ++j)
+                    if (want[j]) send_idx.push_back((int32_t)j);
+                ctx->send_cnt[q] = (int64_t)send_idx.size() - ctx->send_off[q];
+            }
+            ctx->send_rows = (int64_t)send_idx.size();
+        }
+        /* exchange only what is referenced when that is clearly less than everything (structured graphs: a thin
+         * boundary; uniform random graphs at P = 2: nearly all rows, where the plain all-gather is the better tool) */
+        ctx->use_halo = (double)ctx->halo_rows < 0.85 * (double)(n - nl);
+        if (const char *hv = getenv("LORADS_HALO")) ctx->use_halo = atoi(hv) != 0;
+        if (ctx->use_halo) {
+            for (auto &cj : lf_col) cj = remap[cj];
+            dev_free(ctx->send_idx);
+            TRY(dev_upload(ctx, &ctx->send_idx, send_idx));
+        }
         std::vector<double> lmc_val((size_t)(e1 - e0)), lrc_a(rc_a.begin() + k0, rc_a.begin() + k1);
         for (int64_t i = 0; i <= nl; ++i) { lf_ptr[i] = f_ptr[lo + i] - e0; lrc_ptr[i] = rc_ptr[lo + i] - k0; }
         for (int32_t e = e0; e < e1; ++e) lmc_val[e - e0] = cval[f_slot[e]];
@@ -1086,8 +1123,14 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
         TRY(alloc_flat(ctx, &ctx->CD));
     }
     if (ctx->world > 1) {
-        dev_free(ctx->gfull);
-        TRY(dev_alloc(ctx, &ctx->gfull, (size_t)ctx->world * (size_t)ctx->N));
+        dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
+        if (ctx->use_halo) {
+            const size_t ld = (size_t)ctx->cones[0].ld;
+            TRY(dev_alloc(ctx, &ctx->halo, (size_t)ctx->halo_rows * ld));
+            TRY(dev_alloc(ctx, &ctx->sendbuf, (size_t)ctx->send_rows * ld));
+        } else {
+            TRY(dev_alloc(ctx, &ctx->gfull, (size_t)ctx->world * (size_t)ctx->N));
+        }
     }
     ctx->h = lbfgs_len;
     ctx->head = 0;
@@ -1351,14 +1394,6 @@ extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
 /* ------------------------------------------------------------------------------------------------
  * fused MaxCut-type path helpers (ctx->mc: one diag_only cone, every constraint non-zero, no LP)
  * ------------------------------------------------------------------------------------------------*/
-/* all-gather the local rows of X into ctx->gfull (global row order) for the sparse product; one GPU: X itself */
-static const double *mc_gather(lgpu_ctx *ctx, const double *X)
-{
-    if (ctx->world <= 1) return X;
-    g_nccl.AllGather(X, ctx->gfull, (size_t)ctx->N, LG_NCCL_FLOAT64, (lg_ncclComm_t)ctx->comm, ctx->stream);
-    return ctx->gfull;
-}
-
 /* out_k = scale a_k <A_i, B_i> ; with b != nullptr also dsc[SC_PINF] = sum (b - out)^2 */
 static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double scale, double *out, bool with_pinf)
 {
@@ -1370,15 +1405,54 @@ static void mc_rowdot(lgpu_ctx *ctx, const double *A, const double *B, double sc
                       ctx->partials, ctx->counter, ctx->dsc, slot1(SC_PINF, 0)));
     if (with_pinf) allreduce_scalars(ctx, SC_PINF, 1);
 }
-/* T = C X ; X local rows (all-gathered first in a partitioned run) */
+
+/* make the remote factor rows the sparse product references available: either all rows of every rank
+ * (ncclAllGather into gfull, global row order) or only the referenced ones (pack + grouped ncclSend/ncclRecv into
+ * `halo`).  One GPU: nothing to do. */
+static int mc_exchange(lgpu_ctx *ctx, const double *X)
+{
+    if (ctx->world <= 1) return 0;
+    if (!ctx->use_halo) {
+        NC(ctx, g_nccl.AllGather(X, ctx->gfull, (size_t)ctx->N, LG_NCCL_FLOAT64, (lg_ncclComm_t)ctx->comm, ctx->stream));
+        return 0;
+    }
+    DevCone &c = ctx->cones[0];
+    const int G = pick_group(c.ld);
+    if (ctx->send_rows > 0) {
+        Prof pr(ctx, KC_LAYOUT);
+        DISPATCH_G(G, k_pack_rows<GG><<<grid_for(ctx, ctx->send_rows * GG, (const void *)k_pack_rows<GG>), LGPU_TPB, 0, ctx->stream>>>(
+                          ctx->send_rows, (int)c.ld, ctx->send_idx, X, ctx->sendbuf));
+    }
+    NC(ctx, g_nccl.GroupStart());
+    for (int q = 0; q < ctx->world; ++q) {
+        if (q == ctx->rank) continue;
+        if (ctx->send_cnt[q] > 0)
+            NC(ctx, g_nccl.Send(ctx->sendbuf + (size_t)ctx->send_off[q] * c.ld, (size_t)ctx->send_cnt[q] * c.ld, LG_NCCL_FLOAT64, q,
+                                (lg_ncclComm_t)ctx->comm, ctx->stream));
+        if (ctx->recv_cnt[q] > 0)
+            NC(ctx, g_nccl.Recv(ctx->halo + (size_t)ctx->recv_off[q] * c.ld, (size_t)ctx->recv_cnt[q] * c.ld, LG_NCCL_FLOAT64, q,
+                                (lg_ncclComm_t)ctx->comm, ctx->stream));
+    }
+    NC(ctx, g_nccl.GroupEnd());
+    return 0;
+}
+
+/* T = C X ; X = this rank's rows (remote rows exchanged first in a partitioned run) */
 static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
 {
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
-    const double *Xg = mc_gather(ctx, X);
+    if (mc_exchange(ctx, X) != 0) return;
     Prof pr(ctx, KC_MC_SPMM);
-    DISPATCH_G(G, k_mc_spmm<GG, 2><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2>), LGPU_TPB, 0, ctx->stream>>>(
-                      c.n, c.f_ptr, c.f_col, c.mc_val, Xg, (int)c.ld, T));
+    if (ctx->world > 1 && ctx->use_halo) {
+        const double *Xh = ctx->halo - (size_t)c.n_alloc * c.ld; /* halo row k is addressed as column n_alloc + k */
+        DISPATCH_G(G, k_mc_spmm<GG, 2, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, true>), LGPU_TPB, 0, ctx->stream>>>(
+                          c.n, c.f_ptr, c.f_col, c.mc_val, X, Xh, (int)c.n_alloc, (int)c.ld, T));
+    } else {
+        const double *Xg = ctx->world > 1 ? ctx->gfull : X;
+        DISPATCH_G(G, k_mc_spmm<GG, 2, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, false>), LGPU_TPB, 0, ctx->stream>>>(
+                          c.n, c.f_ptr, c.f_col, c.mc_val, Xg, nullptr, 0, (int)c.ld, T));
+    }
 }
 static void mc_refresh_cr(lgpu_ctx *ctx)
 {

@@ -170,7 +170,15 @@ struct lgpu_ctx {
     /* row-block partition over `world` ranks (NCCL); world == 1: single GPU */
     int rank = 0, world = 1;
     void *comm = nullptr;     /* ncclComm_t */
-    double *gfull = nullptr;  /* [world * n_alloc * ld] all-gathered factor rows for the sparse product */
+    double *gfull = nullptr;  /* all-gather mode: [world * n_alloc * ld] factor rows of every rank, global row order */
+    /* halo mode: only the remote rows this rank's CSR rows reference are exchanged (ncclSend/ncclRecv), into
+     * `halo` (rows grouped by owner, ascending); CSR columns are remapped: local row j - lo, halo row n_alloc + k */
+    bool use_halo = false;
+    int64_t halo_rows = 0, send_rows = 0;
+    std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt; /* per peer, in rows */
+    int32_t *send_idx = nullptr; /* [send_rows] local row to pack, grouped by destination */
+    double *sendbuf = nullptr;   /* [send_rows * ld] */
+    double *halo = nullptr;      /* [halo_rows * ld] */
     /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */
     bool dense_dmma = true;   /* dense-aggregate cones: SYR2K / SYMM on the FP64 tensor pipe */
     bool fast_enabled = true;
@@ -205,7 +213,6 @@ struct lgpu_ctx {
     int64_t prof_cnt[KC_COUNT] = {0};
     cudaEvent_t timers[8] = {nullptr};
     /* generic staging for host<->device operator calls */
-    double *hstage = nullptr; size_t hstage_bytes = 0;
     void *dstage = nullptr; size_t dstage_bytes = 0;
 };
 

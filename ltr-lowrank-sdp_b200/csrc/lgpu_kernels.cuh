@@ -296,37 +296,6 @@ __global__ void __launch_bounds__(128) k_dense_symm(int64_t n, int ld, const dou
     }
 }
 
-/* diag_only cones, CG operator: only the diagonal samples are ever read (A_i = a e_d e_d^T)
- * cv[t] = a_t * <U_d, V_d>                 reference: sdp*ConeAUVImpl on 1-entry diagonal constraints */
-template <int G>
-__global__ void __launch_bounds__(LGPU_TPB) k_diag_auv(int64_t mA, const int32_t *__restrict__ drow,
-                                                       const double *__restrict__ dval, const double *__restrict__ U,
-                                                       const double *__restrict__ V, int ld, double *__restrict__ cv)
-{
-    const int lane = threadIdx.x % G;
-    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
-    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int ld2 = ld >> 1;
-    const int64_t iters = (mA + groups - 1) / groups;
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t t = g0 + it * groups;
-        const bool live = t < mA;
-        double a = 0.0;
-        if (live) {
-            const int i = drow[t];
-            const double2 *Ui = reinterpret_cast<const double2 *>(U + (size_t)i * ld);
-            const double2 *Vi = reinterpret_cast<const double2 *>(V + (size_t)i * ld);
-            for (int c = lane; c < ld2; c += G) {
-                double2 u = Ui[c], v = Vi[c];
-                a = fma(u.x, v.x, a);
-                a = fma(u.y, v.y, a);
-            }
-        }
-        a = group_sum<G>(a);
-        if (live && lane == 0) cv[t] = dval[t] * a;
-    }
-}
-
 /* ------------------------------------------------------------------------------------------------
  * K2  per-constraint gather  cv[t] = sum_e coef[e] * uvt[slot[e]]
  *     reference: sdpDenseConeAUVImpl / sdpSparseConeAUVImpl -> sparseAUV / denseAUV,
@@ -434,20 +403,6 @@ __global__ void __launch_bounds__(LGPU_TPB) k_spmm(int64_t n, const int32_t *__r
                 reinterpret_cast<double2 *>(Y + (size_t)i * ld)[c] = o;
             }
         }
-    }
-}
-
-/* CG operator tail for diag_only cones: res = x + Diag(sum_t w_t a_t e_{d_t}) V, via a per-row
- * accumulated diagonal `dg` (length n)          reference: linSysProduct, lorads_admm.c:471-486 */
-__global__ void __launch_bounds__(LGPU_TPB) k_rowscale_add(int64_t n, int ld, const double *__restrict__ dg,
-                                                           const double *__restrict__ V, const double *__restrict__ X,
-                                                           double *__restrict__ out)
-{
-    const int64_t total = n * (int64_t)ld;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t row = i / ld;
-        out[i] = fma(dg[row], V[i], X[i]);
     }
 }
 
@@ -580,12 +535,15 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
  * warps, not per-thread tricks -- the same product with a software-pipelined (column, value) prefetch and 8 loads in
  * flight per lane needed 48-115 registers and ran 1.8-3.9x slower than this 32-register form at 8 CTAs per SM.
  * A group of G lanes owns a row; lane c holds 16-byte column word c; U entries are fetched per trip. */
-template <int G, int U>
+template <int G, int U, bool HALO>
 __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
-                                                                const int32_t *__restrict__ fcol,
-                                                                const double *__restrict__ fval, const double *__restrict__ X,
-                                                                int ld, double *__restrict__ T)
+                                                         const int32_t *__restrict__ fcol, const double *__restrict__ fval,
+                                                         const double *__restrict__ Xin, const double *__restrict__ Xhalo,
+                                                         int nsplit, int ld, double *__restrict__ T)
 {
+    /* HALO: column ids < nsplit address this rank's own rows (Xin), the others the received halo rows; Xhalo is
+     * passed pre-offset by -nsplit rows so both cases index with the column id itself */
+#define X_ROW(col) ((HALO && (col) >= nsplit ? Xhalo : Xin) + (size_t)(col) * ld)
     const int lane = threadIdx.x % G;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -601,18 +559,37 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     v[u] = fval[e + u];
-                    x[u] = reinterpret_cast<const double2 *>(X + (size_t)fcol[e + u] * ld)[c];
+                    const int col = fcol[e + u];
+                    x[u] = reinterpret_cast<const double2 *>(X_ROW(col))[c];
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) { acc.x = fma(v[u], x[u].x, acc.x); acc.y = fma(v[u], x[u].y, acc.y); }
             }
             for (; e < e1; ++e) {
                 const double v = fval[e];
-                const double2 x = reinterpret_cast<const double2 *>(X + (size_t)fcol[e] * ld)[c];
+                const int col = fcol[e];
+                const double2 x = reinterpret_cast<const double2 *>(X_ROW(col))[c];
                 acc.x = fma(v, x.x, acc.x); acc.y = fma(v, x.y, acc.y);
             }
             reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
         }
+    }
+#undef X_ROW
+}
+
+/* pack the rows other ranks need into the send buffer (grouped by destination): out[k] = X[idx[k]] */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_pack_rows(int64_t nrows, int ld, const int32_t *__restrict__ idx,
+                                                        const double *__restrict__ X, double *__restrict__ out)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    for (int64_t k = g0; k < nrows; k += groups) {
+        const size_t src = (size_t)idx[k] * ld2, dst = (size_t)k * ld2;
+        for (int c = lane; c < ld2; c += G)
+            reinterpret_cast<double2 *>(out)[dst + c] = reinterpret_cast<const double2 *>(X)[src + c];
     }
 }
 

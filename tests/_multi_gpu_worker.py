@@ -69,8 +69,12 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl")
-    n, r, iters = 20001, 20, 25          # odd n: ragged last row block
-    ei, ej, w = lb.random_graph(n, 5, 3)
+    if os.environ.get("LORADS_TEST_GRAPH", "random") == "torus":
+        n, r, iters = 101 * 199, 20, 25  # structured: thin halos (the library picks the halo exchange by itself)
+        ei, ej, w = lb.torus_graph(101, 199, 81)
+    else:
+        n, r, iters = 20001, 20, 25      # odd n: ragged last row block; random graph: nearly every remote row is needed
+        ei, ej, w = lb.random_graph(n, 5, 3)
     p = lb.maxcut_problem(n, ei, ej, w)
     rng = np.random.default_rng(925)
     R0 = rng.random((n, r)) - rng.random((n, r))
