@@ -867,7 +867,22 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         }
         /* exchange only what is referenced when that is clearly less than everything (structured graphs: a thin
          * boundary; uniform random graphs at P = 2: nearly all rows, where the plain all-gather is the better tool) */
-        ctx->use_halo = (double)ctx->halo_rows < 0.85 * (double)(n - nl);
+        {
+            /* the choice must be the same on every rank, so it is made from the halo sizes of ALL ranks (each rank
+             * can count them: it holds the whole CSR) */
+            int64_t all_halo = 0;
+            std::vector<uint8_t> seen(n);
+            for (int q = 0; q < P; ++q) {
+                int64_t qlo, qhi, qr;
+                lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
+                std::fill(seen.begin(), seen.end(), 0);
+                for (int32_t e = f_ptr[qlo]; e < f_ptr[qhi]; ++e) {
+                    const int32_t j = f_col[e];
+                    if ((j < qlo || j >= qhi) && !seen[j]) { seen[j] = 1; ++all_halo; }
+                }
+            }
+            ctx->use_halo = (double)all_halo < 0.85 * (double)n * (double)(P - 1);
+        }
         if (const char *hv = getenv("LORADS_HALO")) ctx->use_halo = atoi(hv) != 0;
         if (ctx->use_halo) {
             for (auto &cj : lf_col) cj = remap[cj];
@@ -1883,24 +1898,26 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
         for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
         sp.accumulate = 0;
         Prof pr(ctx, KC_MC_STEP);
-#define MC_STEP(MB)                                                                                                             \
-    DISPATCH_G(G, k_mc_step<GG, true, MB><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, true, MB>), LGPU_TPB, 0,         \
+#define MC_STEP(MB, CS)                                                                                                         \
+    DISPATCH_G(G, k_mc_step<GG, true, MB, CS><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, true, MB, CS>), LGPU_TPB, 0, \
                                             ctx->stream>>>(c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,    \
                                                            ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, \
                                                            ctx->cvs, ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo],          \
                                                            ctx->partials, ctx->counter, ctx->dsc, sp, SC_BETA0 + jn))
         switch (ctx->step_variant) {
-        case 1: MC_STEP(3); break;
-        case 2: MC_STEP(4); break;
-        case 3: MC_STEP(5); break;
-        default: MC_STEP(2); break;
+        case 1: MC_STEP(3, false); break;
+        case 2: MC_STEP(4, false); break;
+        case 3: MC_STEP(5, false); break;
+        case 4: MC_STEP(3, true); break;
+        case 5: MC_STEP(4, true); break;
+        default: MC_STEP(2, false); break;
         }
 #undef MC_STEP
     } else {
         SlotSpec<3> sp;
         sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
         Prof pr(ctx, KC_MC_STEP);
-        DISPATCH_G(G, k_mc_step<GG, false, 4><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, false, 4>), LGPU_TPB, 0, ctx->stream>>>(
+        DISPATCH_G(G, k_mc_step<GG, false, 4, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_step<GG, false, 4, false>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, (int)c.ld, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid,
                           c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials,
                           ctx->counter, ctx->dsc, sp, SC_BETA0 + jn));

@@ -66,7 +66,7 @@ enum {
 /* kernel classes for the live per-launch timing (lgpu_profile_*), bench.py's roofline source */
 enum {
     KC_UVT = 0,     /* k_uvt: pattern samples of sym(U V^T) */
-    KC_GATHER,      /* k_con_gather / objective gather / k_diag_auv */
+    KC_GATHER,      /* k_con_gather / objective gather / k_mc_rowdot / k_mc_epi */
     KC_WSUM,        /* k_wsum: A^*(w) (+C) on the pattern */
     KC_SPMM,        /* k_spmm: S X */
     KC_VEC,         /* flat elementwise kernels */

@@ -32,6 +32,19 @@ __device__ __forceinline__ double group_sum(double v)
     return v;
 }
 
+/* streamed-once data: evict-first loads / stores keep the L2 for what is actually reused (the gathered factor rows) */
+template <bool CS>
+__device__ __forceinline__ double2 ldv(const double *p, size_t w)
+{
+    return CS ? __ldcs(reinterpret_cast<const double2 *>(p) + w) : reinterpret_cast<const double2 *>(p)[w];
+}
+template <bool CS>
+__device__ __forceinline__ void stv(double *p, size_t w, double2 v)
+{
+    if (CS) __stcs(reinterpret_cast<double2 *>(p) + w, v);
+    else reinterpret_cast<double2 *>(p)[w] = v;
+}
+
 template <int K>
 struct SlotSpec {
     int slot[K];
@@ -709,7 +722,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
  *   updateDimacsALM: constrValSum <- A(R R^T) from scratch, |b - A|^2      lorads_alg_common.c:386-394,424-428
  * C R is carried as CR <- CR + tau (C D) with C D = T from k_mc_spmm.
  * reductions: [0] sum Grad^2, [1] <y,s>, [2] sum (b - A(RR^T))^2 */
-template <int G, bool GRAM, int MINB>
+template <int G, bool GRAM, int MINB, bool CS>
 __global__ void __launch_bounds__(LGPU_TPB, MINB) k_mc_step(int64_t n, int ld, double tau, double rho, double *__restrict__ Rm,
                                                       const double *__restrict__ D, double *__restrict__ CR,
                                                       const double *__restrict__ T, double *__restrict__ Gd,
@@ -753,11 +766,11 @@ __global__ void __launch_bounds__(LGPU_TPB, MINB) k_mc_step(int64_t n, int ld, d
             }
             for (int c = lane; c < ld2; c += G) {
                 const size_t w = (size_t)i * ld2 + c;
-                double2 r = reinterpret_cast<double2 *>(Rm)[w];
-                const double2 d = reinterpret_cast<const double2 *>(D)[w];
-                double2 cr = reinterpret_cast<double2 *>(CR)[w];
-                const double2 t = reinterpret_cast<const double2 *>(T)[w];
-                const double2 go = reinterpret_cast<double2 *>(Gd)[w];
+                double2 r = ldv<CS>(Rm, w);
+                const double2 d = ldv<CS>(D, w);
+                double2 cr = ldv<CS>(CR, w);
+                const double2 t = ldv<CS>(T, w);
+                const double2 go = ldv<CS>(Gd, w);
                 r.x = fma(tau, d.x, r.x); r.y = fma(tau, d.y, r.y);
                 cr.x = fma(tau, t.x, cr.x); cr.y = fma(tau, t.y, cr.y);
                 double2 gn;
@@ -765,16 +778,16 @@ __global__ void __launch_bounds__(LGPU_TPB, MINB) k_mc_step(int64_t n, int ld, d
                 gn.y = 2.0 * fma(coef, r.y, cr.y);
                 const double2 sv = make_double2(tau * d.x, tau * d.y);
                 const double2 yv = make_double2(-go.x + gn.x, -go.y + gn.y);
-                reinterpret_cast<double2 *>(Rm)[w] = r;
-                reinterpret_cast<double2 *>(CR)[w] = cr;
-                reinterpret_cast<double2 *>(Gd)[w] = gn;
-                reinterpret_cast<double2 *>(sh)[w] = sv;
-                reinterpret_cast<double2 *>(yh)[w] = yv;
+                stv<CS>(Rm, w, r);
+                stv<CS>(CR, w, cr);
+                stv<CS>(Gd, w, gn);
+                stv<CS>(sh, w, sv);
+                stv<CS>(yh, w, yv);
                 red[0] = fma(gn.x, gn.x, red[0]); red[0] = fma(gn.y, gn.y, red[0]);
                 red[1] = fma(yv.x, sv.x, red[1]); red[1] = fma(yv.y, sv.y, red[1]);
                 if (GRAM) {
-                    const double2 os = reinterpret_cast<const double2 *>(so)[w];
-                    const double2 oy = reinterpret_cast<const double2 *>(yo)[w];
+                    const double2 os = ldv<CS>(so, w);
+                    const double2 oy = ldv<CS>(yo, w);
                     red[3] = fma(gn.x, sv.x, red[3]); red[3] = fma(gn.y, sv.y, red[3]);
                     red[4] = fma(gn.x, yv.x, red[4]); red[4] = fma(gn.y, yv.y, red[4]);
                     red[5] = fma(gn.x, os.x, red[5]); red[5] = fma(gn.y, os.y, red[5]);
