@@ -77,6 +77,8 @@ int lgpu_lp_upload(lgpu_ctx *ctx, const int64_t *lp_beg, const int64_t *lp_idx, 
  * out[0] = #nonzero A_i, out[1] = aggregate is dense, out[2] = SPARSE_CONE container, out[3] = nnzP,
  * out[4] = all constraints are single diagonal entries (MaxCut-type fast path), out[5] = nnzA */
 int lgpu_cone_info(const lgpu_ctx *ctx, int cone, int64_t out[6]);
+/* the same six facts from the reader's arrays alone: pure host code, needs neither a context nor a GPU */
+int lgpu_cone_classify(int64_t n, int64_t m, const int64_t *mat_beg, const int64_t *mat_idx, int64_t out[6]);
 /* aggregated lower pattern of a cone in the reference's order (sorted by (col,row)) */
 int lgpu_cone_pattern(const lgpu_ctx *ctx, int cone, int64_t cap, int32_t *row, int32_t *col);
 /* cal_sdp_const (lorads_solver.c:1457-1485): out = {|C|_1, |C|_2, |C|_inf, |b|_1, |b|_2, |b|_inf(Q2 quirk)} */

@@ -630,6 +630,76 @@ static inline void unpack_lower(int64_t n, int64_t idx, int64_t *row, int64_t *c
     *row = idx - j * (2 * n - j + 1) / 2 + j;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * The reference's storage rules for one cone (pure host code, no device needed):
+ *   coefficient class  ZERO / SPARSE / DENSE by nnz > 10 % of n(n+1)/2        sdpDataMatSetData, lorads_sdp_data.c:1180-1197
+ *   container          SPARSE_CONE iff #non-zero A_i <= 0.3 m                  LUserDataChooseCone, lorads_user_data.c:105-109
+ *   aggregate          dense iff n < 20, or a dense member, or |union pattern| >= 10 % of the triangle
+ *                                                                              AConePresolveData, lorads_sdp_conic.c:1185-1393
+ * plus what this library derives: the union pattern (sorted packed indices; empty when dense), nnzA and whether every
+ * non-zero constraint is one diagonal entry (MaxCut-type, fused path).
+ * ------------------------------------------------------------------------------------------------*/
+struct ConeRules {
+    int obj_type = 0;
+    int64_t mA = 0, nnzA = 0, nnzP = 0;
+    bool sparse_container = false, dense = false, diag_only = false;
+    std::vector<int64_t> pat;
+};
+static void cone_rules(int64_t n, int64_t m, const int64_t *beg, const int64_t *idx, ConeRules &r)
+{
+    const int64_t tri = n * (n + 1) / 2;
+    auto mtype = [&](int64_t nnz) -> int {
+        if (nnz == 0) return 0;
+        if ((double)nnz > 0.1 * (double)tri) return 2;
+        return 1;
+    };
+    r.obj_type = mtype(beg[1] - beg[0]);
+    bool any_dense = r.obj_type == 2;
+    r.mA = 0;
+    bool diag_only = true;
+    for (int64_t col = 1; col <= m; ++col) {
+        const int64_t nnz = beg[col + 1] - beg[col];
+        if (nnz > 0) ++r.mA;
+        if (mtype(nnz) == 2) any_dense = true;
+        if (nnz > 1) diag_only = false;
+        if (nnz == 1 && diag_only) {
+            int64_t rr, cc;
+            unpack_lower(n, idx[beg[col]], &rr, &cc);
+            if (rr != cc) diag_only = false;
+        }
+    }
+    r.diag_only = diag_only && r.mA > 0;
+    r.nnzA = beg[m + 1] - beg[1];
+    r.sparse_container = !((double)r.mA > 0.3 * (double)m);
+    r.dense = (n < 20) || any_dense;
+    r.pat.clear();
+    if (!r.dense) {
+        r.pat.assign(idx, idx + beg[m + 1]);
+        std::sort(r.pat.begin(), r.pat.end());
+        r.pat.erase(std::unique(r.pat.begin(), r.pat.end()), r.pat.end());
+        if ((double)r.pat.size() / (double)tri >= 0.1) {
+            r.dense = true;
+            r.pat.clear();
+        }
+    }
+    r.nnzP = r.dense ? tri : (int64_t)r.pat.size();
+}
+
+/* the same facts lgpu_cone_info reports after an upload, computed without a context or a GPU */
+extern "C" int lgpu_cone_classify(int64_t n, int64_t m, const int64_t *mat_beg, const int64_t *mat_idx, int64_t out[6])
+{
+    if (n <= 0 || m <= 0 || !mat_beg || !out) return 1;
+    ConeRules r;
+    cone_rules(n, m, mat_beg, mat_idx, r);
+    out[0] = r.mA;
+    out[1] = r.dense ? 1 : 0;
+    out[2] = r.sparse_container ? 1 : 0;
+    out[3] = r.nnzP;
+    out[4] = r.diag_only ? 1 : 0;
+    out[5] = r.nnzA;
+    return 0;
+}
+
 extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, const int64_t *idx_in, const double *val_in)
 {
     if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
@@ -657,31 +727,16 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
             std::copy(tv.begin(), tv.end(), val.begin() + e0);
         }
     }
-    /* storage classes (sdpDataMatSetData, lorads_sdp_data.c:1180-1197) */
-    auto mtype = [&](int64_t nnz) -> int {
-        if (nnz == 0) return 0;
-        if ((double)nnz > 0.1 * (double)tri) return 2;
-        return 1;
-    };
-    c.obj_type = mtype(beg[1] - beg[0]);
-    bool any_dense = c.obj_type == 2;
-    int64_t mA = 0;
-    for (int64_t col = 1; col <= m; ++col) {
-        const int64_t nnz = beg[col + 1] - beg[col];
-        if (nnz > 0) ++mA;
-        if (mtype(nnz) == 2) any_dense = true;
-    }
+    /* storage rules of the reference, shared with the GPU-less lgpu_cone_classify */
+    ConeRules rules;
+    cone_rules(n, m, beg, idx.data(), rules);
+    c.obj_type = rules.obj_type;
+    const int64_t mA = rules.mA;
     c.mA = mA;
-    c.sparse_container = !((double)mA > 0.3 * (double)m); /* LUserDataChooseCone, lorads_user_data.c:105-109 */
-    /* aggregate: dense if n < 20, any dense member, or |union| >= 10% of the triangle (AConePresolveData) */
-    bool dense = (n < 20) || any_dense;
+    c.sparse_container = rules.sparse_container;
+    bool dense = rules.dense;
     std::vector<int64_t> pat;
-    if (!dense) {
-        pat = idx;
-        std::sort(pat.begin(), pat.end());
-        pat.erase(std::unique(pat.begin(), pat.end()), pat.end());
-        if ((double)pat.size() / (double)tri >= 0.1) dense = true;
-    }
+    pat.swap(rules.pat);
     c.dense_aggregate = dense;
     if (dense) {
         if (tri >= (int64_t)1 << 30) LGPU_FAIL(ctx, "dense aggregate too large for this build (n=%lld)", (long long)n);

@@ -90,6 +90,7 @@ def lib() -> ctypes.CDLL:
         "lgpu_cone_upload": (i, [_vp, i, _c_lp, _c_lp, _c_dp]),
         "lgpu_lp_upload": (i, [_vp, _c_lp, _c_lp, _c_dp]),
         "lgpu_cone_info": (i, [_vp, i, _c_lp]),
+        "lgpu_cone_classify": (i, [i64, i64, _c_lp, _c_lp, _c_lp]),
         "lgpu_cone_pattern": (i, [_vp, i, i64, _c_ip, _c_ip]),
         "lgpu_constants": (i, [_vp, _c_dp]),
         "lgpu_obj_scale": (i, [_vp, d]),
@@ -193,6 +194,15 @@ class SdpaProblem:
     @property
     def ncones(self) -> int:
         return len(self.dims)
+
+
+def cone_classify(p: "SdpaProblem", c: int) -> dict:
+    """the reference's storage rules for cone c, computed on the host without a GPU (lgpu_cone_classify)"""
+    o = np.zeros(6, np.int64)
+    if lib().lgpu_cone_classify(int(p.dims[c]), p.m, _i64(p.mat_beg[c]), _i64(p.mat_idx[c]), _i64(o)) != 0:
+        raise LoradsError("lgpu_cone_classify failed")
+    return dict(nnz_rows=int(o[0]), dense_aggregate=bool(o[1]), sparse_container=bool(o[2]), nnzP=int(o[3]),
+                diag_only=bool(o[4]), nnzA=int(o[5]))
 
 
 def partition_rows(n: int, world: int, rank: int):

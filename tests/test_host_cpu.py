@@ -150,3 +150,34 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".c", ".h", ".cu", ".cuh")) or fn == "Makefile":
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "lorads_oracle" not in txt and "oracle/" not in txt and "lorads_ref" not in txt, fn
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_storage_rules_without_gpu(built, name):
+    """lgpu_cone_classify (pure host) reproduces the reference's container / aggregate classes recorded in the golden
+    vectors, and the pattern size / non-zero constraint count of the oracle's cone."""
+    from conftest import golden
+    g = golden(name)
+    p = built.read_sdpa(inst_path(name))
+    q = orc.read_sdpa(inst_path(name))
+    for c, blk in enumerate(q.blocks):
+        cone = orc.build_cone(blk, q.m)
+        info = built.cone_classify(p, c)
+        assert info["sparse_container"] == bool(g["sparse_container"][c])
+        assert info["dense_aggregate"] == bool(g["dense_aggregate"][c])
+        assert info["nnz_rows"] == cone.nnz_rows and info["nnzP"] == cone.nnzP
+        assert info["nnzA"] == len(cone.a_slot)
+        is_maxcut = name in ("G11", "maxcut_torus_8x10", "maxcut_torus_20x30")
+        assert info["diag_only"] == is_maxcut
+
+
+def test_synthetic_builders(built):
+    lb = built
+    ei, ej, w = lb.random_graph(5000, 5, 0)
+    assert np.all(ei < ej) and len(np.unique(ei * 5000 + ej)) == len(ei)       # unique undirected edges
+    p = lb.maxcut_problem(5000, ei, ej, w)
+    info = lb.cone_classify(p, 0)
+    assert info["diag_only"] and not info["dense_aggregate"] and info["nnz_rows"] == 5000
+    assert info["nnzP"] == len(ei) + 5000
+    ti, tj, tw = lb.torus_graph(100, 200, 81)
+    assert len(ti) == 40000 and set(np.unique(tw)) == {-1.0, 1.0}              # G81-like: 2 edges per vertex
