@@ -526,9 +526,10 @@ def pack_idx(n, i, j):
 
 
 def maxcut_problem(n: int, ei: np.ndarray, ej: np.ndarray, w: np.ndarray) -> SdpaProblem:
-    """MaxCut SDP of a weighted graph in the gen_MaxCut.jl file convention (lorads/data/gen_MaxCut.jl):
-    F0 = -L/2 (off-diagonal w_ij/2, diagonal -deg_i/2), A_k = e_k e_k^T, b = 1; the reader negates F0
-    (lorads_file_io.c:317-319), so the arrays below hold C = -F0.  Edges must be unique with ei != ej."""
+    """MaxCut SDP of a weighted graph in the gen_MaxCut.jl file convention (lorads/data/gen_MaxCut.jl:225-229 and the
+    bundled G11.dat-s): the file holds F0 = L/2 (off-diagonal -w_ij/2, diagonal +deg_i/2), A_k = e_k e_k^T, b = 1; the
+    reader negates F0 (lorads_file_io.c:317-319), so LoRADS minimises <C, X> with C = -L/2 (= -2 x the MaxCut SDP value at
+    the optimum; G1: -24166.3).  The arrays below hold C.  Edges must be unique with ei != ej."""
     ei = np.asarray(ei, dtype=np.int64)
     ej = np.asarray(ej, dtype=np.int64)
     w = np.asarray(w, dtype=np.float64)
@@ -538,7 +539,7 @@ def maxcut_problem(n: int, ei: np.ndarray, ej: np.ndarray, w: np.ndarray) -> Sdp
     np.add.at(deg, hi, w)
     dnz = np.nonzero(deg)[0].astype(np.int64)
     idx = np.concatenate([pack_idx(n, hi, lo), pack_idx(n, dnz, dnz)])
-    val = np.concatenate([-0.5 * w, 0.5 * deg[dnz]])
+    val = np.concatenate([0.5 * w, -0.5 * deg[dnz]])
     o = np.argsort(idx, kind="stable")
     idx, val = idx[o], val[o]
     k = np.arange(n, dtype=np.int64)
