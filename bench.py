@@ -230,9 +230,12 @@ def time_to_tolerance(lb, with_reference=True):
                 inner = int(line.split("InnerIter:")[1].split()[0])
             elif line.startswith("all_time:"):
                 all_time = float(line.split(":")[1])
+            elif line.startswith("all_dual_infea:"):
+                parse.dual = float(line.split(":")[1])
             elif "1.Primal Objective:" in line:
                 obj = float(line.split(":")[-1])
         return inner, all_time, obj
+    parse.dual = None
 
     res = {"workload": "G81-like 100x200 +-1 torus MaxCut, n=m=20000 (BASELINE configs[2] stand-in), "
                        "--phase1Tol 1e-2 --heuristicFactor 10 --reoptLevel 0, default rank rule (20)"}
@@ -240,7 +243,8 @@ def time_to_tolerance(lb, with_reference=True):
     mine = lb.run_solver([inst] + flags + ["--jsonfile", os.path.join(d, "mine.json")], timeout=900)
     res["ours_process_wall_s"] = time.perf_counter() - t0
     it, at, obj = parse(mine.stdout)
-    res.update({"ours_solve_s": at, "ours_alm_inner_iters": it, "ours_primal_obj": obj, "ours_exit": mine.returncode})
+    res.update({"ours_solve_s": at, "ours_dual_infeasibility_s": parse.dual, "ours_alm_inner_iters": it,
+                "ours_primal_obj": obj, "ours_exit": mine.returncode})
     ref = os.path.join(ROOT, "oracle", "_ref", "lorads_ref")
     if with_reference and os.path.exists(ref):
         env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
@@ -248,8 +252,8 @@ def time_to_tolerance(lb, with_reference=True):
         theirs = subprocess.run([ref, inst] + flags, capture_output=True, text=True, timeout=900, env=env)
         res["reference_process_wall_s"] = time.perf_counter() - t0
         it, at, obj = parse(theirs.stdout)
-        res.update({"reference_solve_s": at, "reference_alm_inner_iters": it, "reference_primal_obj": obj,
-                    "reference_cores": 1})
+        res.update({"reference_solve_s": at, "reference_dual_infeasibility_s": parse.dual,
+                    "reference_alm_inner_iters": it, "reference_primal_obj": obj, "reference_cores": 1})
         if at and res["ours_solve_s"]:
             res["speedup_solve"] = at / res["ours_solve_s"]
     return res

@@ -2396,7 +2396,9 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
 /* ------------------------------------------------------------------------------------------------
  * dual infeasibility: lambda_min(C - A*(lambda)) per cone by Lanczos on the device
  * ------------------------------------------------------------------------------------------------*/
-static double tridiag_min_eig(const std::vector<double> &a, const std::vector<double> &b, int k)
+/* extreme eigenvalue of the k x k Lanczos tridiagonal (diagonal a, off-diagonal b) by Sturm bisection;
+ * which = -1: smallest, +1: largest */
+static double tridiag_extreme_eig(const std::vector<double> &a, const std::vector<double> &b, int k, int which)
 {
     double lo = a[0], hi = a[0];
     for (int i = 0; i < k; ++i) {
@@ -2406,6 +2408,7 @@ static double tridiag_min_eig(const std::vector<double> &a, const std::vector<do
         lo = std::min(lo, a[i] - rr);
         hi = std::max(hi, a[i] + rr);
     }
+    const int target = which < 0 ? 1 : k; /* number of eigenvalues < x we bracket */
     for (int it = 0; it < 200; ++it) {
         const double mid = 0.5 * (lo + hi);
         int cnt = 0;
@@ -2416,12 +2419,63 @@ static double tridiag_min_eig(const std::vector<double> &a, const std::vector<do
             d = a[i] - mid - b[i - 1] * b[i - 1] / dd;
             if (d < 0) cnt++;
         }
-        if (cnt >= 1) hi = mid; else lo = mid;
+        if (cnt >= target) hi = mid; else lo = mid;
         if (hi - lo <= 1e-15 * (fabs(lo) + fabs(hi)) + 1e-300) break;
     }
     return 0.5 * (lo + hi);
 }
+/* |last component| of the unit eigenvector of T_k for eigenvalue theta (three-term recurrence, rescaled as it goes):
+ * times beta_k it is the residual norm of the Ritz pair */
+static double tridiag_last_component(const std::vector<double> &a, const std::vector<double> &b, int k, double theta)
+{
+    if (k == 1) return 1.0;
+    double vm = 0.0, v = 1.0, nrm2 = 1.0;
+    for (int i = 0; i < k - 1; ++i) {
+        const double bi = (b[i] == 0.0) ? 1e-300 : b[i];
+        double vn = ((theta - a[i]) * v - (i > 0 ? b[i - 1] * vm : 0.0)) / bi;
+        vm = v;
+        v = vn;
+        nrm2 += v * v;
+        if (nrm2 > 1e200) { const double sc = 1e-100; vm *= sc; v *= sc; nrm2 *= sc * sc; }
+    }
+    return fabs(v) / sqrt(nrm2);
+}
 
+/* re-orthogonalisation of w against the first k basis vectors in two launches: h = Q^T w (one block per basis
+ * vector, fixed summation order), then w -= Q h */
+__global__ void __launch_bounds__(LGPU_TPB) k_basis_dots(int64_t n, const double *__restrict__ Q, const double *__restrict__ w,
+                                                         double *__restrict__ h)
+{
+    __shared__ double sh[LGPU_TPB / 32];
+    const double *q = Q + (size_t)blockIdx.x * n;
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += LGPU_TPB) a = fma(q[i], w[i], a);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < LGPU_TPB / 32; ++k) t += sh[k];
+        h[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(LGPU_TPB) k_basis_update(int64_t n, int k, const double *__restrict__ Q,
+                                                           const double *__restrict__ h, double *__restrict__ w)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = w[i];
+        for (int j = 0; j < k; ++j) a = fma(-h[j], Q[(size_t)j * n + i], a);
+        w[i] = a;
+    }
+}
+
+/* calculate_dual_infeasibility_solver (lorads_solver.c:1396-1426, lorads_sdp_conic.c:1636-1699): the reference asks
+ * ARPACK (dsaupd/dseupd, "SA", nev = 1, tol = 1e-2) for lambda_min(C - A^*(lambda)) of every cone.  Here: Lanczos on the
+ * device, S applied through the full symmetric CSR (sdp_coeff.mv, lorads_sdp_data.c:772-787,983-1006), stopped on the
+ * Ritz residual |beta_k s_k| <= 1e-6 x (spectral scale of T_k).  Small cones keep the whole Krylov basis and
+ * re-orthogonalise against it (two launches per step); large ones run the plain three-term recurrence, whose extreme
+ * Ritz value stays accurate without it. */
 extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
 {
     if (!ctx || !ctx->vars_ready) return 1;
@@ -2442,19 +2496,19 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
     double *dsc = ctx->dsc;
     for (auto &c : ctx->cones) {
         const int64_t n = c.n;
-        int kmax = (int)std::min<int64_t>(n, 300);
-        {
-            const int64_t by_mem = (int64_t)(6.0e9 / (8.0 * (double)n)) - 2; /* keep the Krylov basis under ~6 GB */
-            if (by_mem < kmax) kmax = (int)std::max<int64_t>(by_mem, 20);
-        }
+        const int kmax = (int)std::min<int64_t>(n, 300);
+        const bool full = (double)n * (double)(kmax + 1) * 8.0 <= 256.0e6; /* keep the basis only while it is small */
         /* slack S = C - sum lambda_i A_i on the pattern */
         run_wsum(ctx, c, ctx->lam, true, true, -1.0, c.S);
         const size_t vec = (size_t)n;
-        TRY(ensure_dstage(ctx, sizeof(double) * vec * ((size_t)kmax + 2)));
-        double *Q = (double *)ctx->dstage;
-        double *w = Q + vec * ((size_t)kmax + 1);
+        const size_t nvec = full ? (size_t)kmax + 2 : 4;
+        TRY(ensure_dstage(ctx, sizeof(double) * (vec * nvec + (size_t)kmax + 8)));
+        double *Q = (double *)ctx->dstage;       /* full: q_0 .. q_kmax ; else ring of 3 */
+        double *w = Q + vec * (nvec - 1);
+        double *hbuf = w + vec;
+        auto qptr = [&](int k) { return Q + vec * (size_t)(full ? k : (k % 3)); };
         {
-            double *q0 = Q;
+            double *q0 = qptr(0);
             launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
                 uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
                 z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
@@ -2465,40 +2519,44 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
             launch_map(ctx, n, [=] __device__(int64_t i) { q0[i] /= sqrt(dsc[SC_LANCZOS]); });
         }
         std::vector<double> al, be;
-        double theta = 0.0, theta_prev = 1e300;
+        double theta = 0.0;
         const int32_t *fp = c.f_ptr, *fc = c.f_col, *fs = c.f_slot;
         const double *Sv = c.S;
         for (int k = 0; k < kmax; ++k) {
-            double *qk = Q + vec * (size_t)k;
-            /* w = S q_k  (sdp_coeff.mv, lorads_sdp_data.c:772-787,983-1006) and alpha_k = <q_k, w> */
+            const double *qk = qptr(k);
+            const double *qm = k > 0 ? qptr(k - 1) : nullptr;
+            const double bprev = k > 0 ? be[k - 1] : 0.0;
+            /* w = S q_k - beta_{k-1} q_{k-1} and alpha_k = <q_k, S q_k> */
             launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
                 double a = 0.0;
                 for (int e = fp[i]; e < fp[i + 1]; ++e) a = fma(Sv[fs[e]], qk[fc[e]], a);
-                w[i] = a;
                 acc[0] = fma(qk[i], a, acc[0]);
+                w[i] = qm ? fma(-bprev, qm[i], a) : a;
             }, slot1(SC_LANCZOS));
-            CHECK_LAUNCH(ctx);
-            TRY(fetch_scalars(ctx, SC_LANCZOS, 1));
-            al.push_back(ctx->hsc[SC_LANCZOS]);
-            /* full re-orthogonalisation, twice */
-            for (int pass = 0; pass < 2; ++pass)
-                for (int j = 0; j <= k; ++j) {
-                    const double *qj = Q + vec * (size_t)j;
-                    launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(qj[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 1));
-                    launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS + 1], qj[i], w[i]); });
+            /* w -= alpha_k q_k ; then (small cones) against the whole basis ; beta_k = |w| */
+            launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS], qk[i], w[i]); });
+            if (full) {
+                {
+                    Prof pr(ctx, KC_REDUCE);
+                    k_basis_dots<<<k + 1, LGPU_TPB, 0, ctx->stream>>>(n, Q, w, hbuf);
                 }
-            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 2));
+                {
+                    Prof pr(ctx, KC_VEC);
+                    k_basis_update<<<grid_for(ctx, n, (const void *)k_basis_update), LGPU_TPB, 0, ctx->stream>>>(n, k + 1, Q, hbuf, w);
+                }
+            }
+            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 1));
             CHECK_LAUNCH(ctx);
-            TRY(fetch_scalars(ctx, SC_LANCZOS + 2, 1));
-            const double bnorm = sqrt(ctx->hsc[SC_LANCZOS + 2]);
+            TRY(fetch_scalars(ctx, SC_LANCZOS, 2));
+            al.push_back(ctx->hsc[SC_LANCZOS]);
+            const double bnorm = sqrt(ctx->hsc[SC_LANCZOS + 1]);
             be.push_back(bnorm);
-            theta_prev = theta;
-            theta = tridiag_min_eig(al, be, k + 1);
-            bool conv = false;
-            if (k >= 1 && fabs(theta - theta_prev) <= 1e-6 * (fabs(theta) + 1e-12)) conv = true;
-            if (bnorm <= 1e-14 * (fabs(al.back()) + 1.0)) conv = true;
-            if (conv || k + 1 >= kmax) break;
-            double *qn = Q + vec * (size_t)(k + 1);
+            theta = tridiag_extreme_eig(al, be, k + 1, -1);
+            const double top = tridiag_extreme_eig(al, be, k + 1, +1);
+            const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
+            const double resid = bnorm * tridiag_last_component(al, be, k + 1, theta);
+            if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale || k + 1 >= kmax) break;
+            double *qn = qptr(k + 1);
             const double inv = 1.0 / bnorm;
             launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * inv; });
         }

@@ -223,14 +223,17 @@ def test_dual_infeasibility(lb, name):
     lam = g["lam1"]
     ctx.set_vec(lb.VEC_DUAL, lam)
     got = ctx.dual_infeasibility()
-    want = 0.0
+    want, scale = 0.0, 0.0
     for cone in cones:
         S = orc.wsum(cone, -lam, True)
         M = np.zeros((cone.n, cone.n))
         M[cone.pat_row, cone.pat_col] = S
         M[cone.pat_col, cone.pat_row] = S
-        want += abs(min(np.linalg.eigvalsh(M)[0], 0.0))
-    assert abs(got - want) <= 1e-6 * max(1.0, want), (got, want)
+        ev = np.linalg.eigvalsh(M)
+        want += abs(min(ev[0], 0.0))
+        scale += max(abs(ev[0]), abs(ev[-1]))
+    # the Lanczos stops on a Ritz residual of 1e-6 x the spectral scale (the reference's ARPACK call asks for 1e-2)
+    assert abs(got - want) <= 1e-5 * (1.0 + scale), (got, want, scale)
     ctx.close()
 
 
