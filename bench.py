@@ -264,7 +264,7 @@ def run_reference(args):
     if rank != 0:
         return
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    r = reference_rate(args, max(args.steps, 1) * 2, args.warmup)
+    r = reference_rate(args, max(args.steps, 1), args.warmup)
     if r is None:
         emit({"impl": "reference", "unavailable": "oracle/_ref/liblorads_ref.so is not built"})
         return
