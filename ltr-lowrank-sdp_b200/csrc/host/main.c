@@ -296,6 +296,8 @@ int lorads_b200_main(int argc, char **argv)
         }
     }
     if (lh_setup_problem(S, &data, &params) != LH_RET_OK) { exit_code = 3; goto cleanup; }
+    const int want_profile = getenv("LORADS_PROFILE") != NULL; /* per-kernel-class device time, printed at the end */
+    if (want_profile) lgpu_profile_enable(S->gpu, 1);
     lh_determine_rank(S, &params);
     if (lh_init_variables(S, &params) != LH_RET_OK) { exit_code = 3; goto cleanup; }
 
@@ -418,6 +420,15 @@ end_solving: {
     printf("all_dual_infea: %f\n", all_dual_infea);
     printf("all_time: %f\n", all_time);
     printf("gpu kernel launches: %lld\n", (long long)lgpu_launch_count(S->gpu));
+    if (want_profile) {
+        double ms[32];
+        int64_t cnt[32];
+        const int nc = lgpu_profile_num_classes();
+        if (nc <= 32 && lgpu_profile_read(S->gpu, nc, ms, cnt) == 0)
+            for (int k = 0; k < nc; ++k)
+                if (cnt[k] > 0)
+                    printf("profile %-14s launches %9lld  device ms %12.3f\n", lgpu_profile_class_name(k), (long long)cnt[k], ms[k]);
+    }
     goto cleanup;
 }
 close_log:

@@ -405,6 +405,12 @@ static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, con
     Prof pr(ctx, KC_SPMM);
     DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG, (const void *)k_spmm<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, c.f_ptr, c.f_col, c.f_slot, S, X, (int)ld, alpha, beta, Z, Y));
+    if (c.n_long > 0) {
+        const int blocks = (int)std::min<int64_t>(c.n_long, (int64_t)ctx->num_sms * 4);
+        DISPATCH_G(G, k_spmm_long_rows<GG, false><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
+                          c.n_long, c.long_rows, c.f_ptr, c.f_col, c.f_slot, S, X, nullptr, 0, (int)ld, alpha, beta, Z, Y));
+        ctx->launches++;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -519,6 +525,7 @@ static void free_cone(DevCone &c)
     dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid);
     dev_free(c.t_ptr); dev_free(c.t_loc); dev_free(c.t_gid); dev_free(c.t_val);
     dev_free(c.f_ptr); dev_free(c.f_col); dev_free(c.f_slot); dev_free(c.d_row); dev_free(c.d_val);
+    dev_free(c.long_rows); c.n_long = 0;
     dev_free(c.mc_val); dev_free(c.rc_ptr); dev_free(c.rc_gid); dev_free(c.rc_a);
     dev_free(c.uvt); dev_free(c.S); dev_free(c.cv); dev_free(c.wtmp);
 }
@@ -683,6 +690,18 @@ static void cone_rules(int64_t n, int64_t m, const int64_t *beg, const int64_t *
         }
     }
     r.nnzP = r.dense ? tri : (int64_t)r.pat.size();
+}
+
+/* list of the CSR rows that k_spmm_long_rows takes over */
+static int upload_long_rows(lgpu_ctx *ctx, DevCone &c, const std::vector<int32_t> &ptr)
+{
+    std::vector<int32_t> lr;
+    for (size_t i = 0; i + 1 < ptr.size(); ++i)
+        if (ptr[i + 1] - ptr[i] > LGPU_LONG_ROW) lr.push_back((int32_t)i);
+    c.n_long = (int64_t)lr.size();
+    dev_free(c.long_rows);
+    if (!lr.empty()) TRY(dev_upload(ctx, &c.long_rows, lr));
+    return 0;
 }
 
 /* the same facts lgpu_cone_info reports after an upload, computed without a context or a GPU */
@@ -947,6 +966,7 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         std::vector<double> lmc_val((size_t)(e1 - e0)), lrc_a(rc_a.begin() + k0, rc_a.begin() + k1);
         for (int64_t i = 0; i <= nl; ++i) { lf_ptr[i] = f_ptr[lo + i] - e0; lrc_ptr[i] = rc_ptr[lo + i] - k0; }
         for (int32_t e = e0; e < e1; ++e) lmc_val[e - e0] = cval[f_slot[e]];
+        TRY(upload_long_rows(ctx, c, lf_ptr));
         TRY(dev_upload(ctx, &c.f_ptr, lf_ptr));
         TRY(dev_upload(ctx, &c.f_col, lf_col));
         TRY(dev_upload(ctx, &c.mc_val, lmc_val));
@@ -974,6 +994,7 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     TRY(dev_upload(ctx, &c.t_loc, t_loc));
     TRY(dev_upload(ctx, &c.t_gid, t_gid));
     TRY(dev_upload(ctx, &c.t_val, t_val));
+    TRY(upload_long_rows(ctx, c, f_ptr));
     TRY(dev_upload(ctx, &c.f_ptr, f_ptr));
     TRY(dev_upload(ctx, &c.f_col, f_col));
     TRY(dev_upload(ctx, &c.f_slot, f_slot));
@@ -1518,10 +1539,23 @@ static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
         const double *Xh = ctx->halo - (size_t)c.n_alloc * c.ld; /* halo row k is addressed as column n_alloc + k */
         DISPATCH_G(G, k_mc_spmm<GG, 2, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, true>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, c.f_ptr, c.f_col, c.mc_val, X, Xh, (int)c.n_alloc, (int)c.ld, T));
+        if (c.n_long > 0) {
+            const int blocks = (int)std::min<int64_t>(c.n_long, (int64_t)ctx->num_sms * 4);
+            DISPATCH_G(G, k_spmm_long_rows<GG, true><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
+                              c.n_long, c.long_rows, c.f_ptr, c.f_col, nullptr, c.mc_val, X, Xh, (int)c.n_alloc, (int)c.ld, 1.0, 0.0,
+                              nullptr, T));
+            ctx->launches++;
+        }
     } else {
         const double *Xg = ctx->world > 1 ? ctx->gfull : X;
         DISPATCH_G(G, k_mc_spmm<GG, 2, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, false>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, c.f_ptr, c.f_col, c.mc_val, Xg, nullptr, 0, (int)c.ld, T));
+        if (c.n_long > 0) {
+            const int blocks = (int)std::min<int64_t>(c.n_long, (int64_t)ctx->num_sms * 4);
+            DISPATCH_G(G, k_spmm_long_rows<GG, false><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
+                              c.n_long, c.long_rows, c.f_ptr, c.f_col, nullptr, c.mc_val, Xg, nullptr, 0, (int)c.ld, 1.0, 0.0, nullptr, T));
+            ctx->launches++;
+        }
     }
 }
 static void mc_refresh_cr(lgpu_ctx *ctx)
@@ -2441,6 +2475,30 @@ static double tridiag_last_component(const std::vector<double> &a, const std::ve
     return fabs(v) / sqrt(nrm2);
 }
 
+/* Lanczos step: w = S q - bprev qm and alpha = <q, S q>, one warp per row of the symmetric CSR (lanes stride over the
+ * row's entries, so a hub row of thousands of entries costs ~n/32 steps instead of n)
+ *     reference: sdp_coeff.mv = dataMatSparseMV / dataMatDenseMV, lorads_sdp_data.c:772-787,983-1006 */
+__global__ void __launch_bounds__(LGPU_TPB) k_lanczos_symv(int64_t n, const int32_t *__restrict__ fp, const int32_t *__restrict__ fc,
+                                                           const int32_t *__restrict__ fs, const double *__restrict__ Sv,
+                                                           const double *__restrict__ q, const double *__restrict__ qm,
+                                                           double bprev, double *__restrict__ w, double *partials,
+                                                           unsigned int *counter, double *dsc, SlotSpec<1> spec)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double red[1] = {0.0};
+    for (int64_t i = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += warps) {
+        double a = 0.0;
+        for (int e = fp[i] + lane; e < fp[i + 1]; e += 32) a = fma(Sv[fs[e]], q[fc[e]], a);
+        a = warp_sum(a);
+        if (lane == 0) {
+            red[0] = fma(q[i], a, red[0]);
+            w[i] = qm ? fma(-bprev, qm[i], a) : a;
+        }
+    }
+    grid_reduce_finish<1>(red, partials, counter, dsc, spec);
+}
+
 /* re-orthogonalisation of w against the first k basis vectors in two launches: h = Q^T w (one block per basis
  * vector, fixed summation order), then w -= Q h */
 __global__ void __launch_bounds__(LGPU_TPB) k_basis_dots(int64_t n, const double *__restrict__ Q, const double *__restrict__ w,
@@ -2527,12 +2585,11 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
             const double *qm = k > 0 ? qptr(k - 1) : nullptr;
             const double bprev = k > 0 ? be[k - 1] : 0.0;
             /* w = S q_k - beta_{k-1} q_{k-1} and alpha_k = <q_k, S q_k> */
-            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
-                double a = 0.0;
-                for (int e = fp[i]; e < fp[i + 1]; ++e) a = fma(Sv[fs[e]], qk[fc[e]], a);
-                acc[0] = fma(qk[i], a, acc[0]);
-                w[i] = qm ? fma(-bprev, qm[i], a) : a;
-            }, slot1(SC_LANCZOS));
+            {
+                Prof pr(ctx, KC_SPMM);
+                k_lanczos_symv<<<grid_for(ctx, n * 32, (const void *)k_lanczos_symv), LGPU_TPB, 0, ctx->stream>>>(
+                    n, fp, fc, fs, Sv, qk, qm, bprev, w, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_LANCZOS));
+            }
             /* w -= alpha_k q_k ; then (small cones) against the whole basis ; beta_k = |w| */
             launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS], qk[i], w[i]); });
             if (full) {

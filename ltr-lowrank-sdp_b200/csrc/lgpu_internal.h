@@ -116,6 +116,7 @@ struct DevCone {
     int32_t *con_gid = nullptr;                  /* [mA] global constraint index */
     int32_t *t_ptr = nullptr, *t_loc = nullptr, *t_gid = nullptr; double *t_val = nullptr; /* by slot */
     int32_t *f_ptr = nullptr, *f_col = nullptr, *f_slot = nullptr; /* full CSR */
+    int32_t *long_rows = nullptr; int64_t n_long = 0;               /* rows with > LGPU_LONG_ROW entries */
     int32_t *d_row = nullptr; double *d_val = nullptr; /* diag_only: row and value per constraint */
     /* diag_only fused path: C per full-CSR entry, and row -> constraints (global id, a_k) */
     double *mc_val = nullptr;

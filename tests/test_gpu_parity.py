@@ -322,6 +322,53 @@ def test_dense_cone_tensor_path(lb, tmp_path, n, r):
     assert rel(res[True][3], res[False][3]) < KTOL
 
 
+def test_hub_rows_long_row_kernel(lb, tmp_path):
+    """A hub vertex (one CSR row of n - 1 entries, as in ice_2.0 / checker / p_auss) is handled by the one-CTA-per-row
+    kernel: operator parity against the oracle and fused-vs-general agreement over ALM iterations."""
+    n, r = 3001, 12
+    rng = np.random.default_rng(4)
+    hub_i, hub_j = np.zeros(n - 1, np.int64), np.arange(1, n, dtype=np.int64)
+    ri = rng.integers(1, n, size=4 * n)
+    rj = rng.integers(1, n, size=4 * n)
+    keep = ri < rj
+    key = np.unique(ri[keep] * n + rj[keep])
+    ei = np.concatenate([hub_i, key // n])
+    ej = np.concatenate([hub_j, key % n])
+    w = rng.choice([-1.0, 1.0], size=len(ei))
+    p = lb.maxcut_problem(n, ei, ej, w)
+    f = tmp_path / "hub.dat-s"
+    lb.write_sdpa(str(f), p)
+    q = orc.read_sdpa(str(f))
+    cone = orc.build_cone(q.blocks[0], q.m)
+    X = rng.normal(size=(n, r))
+    wv = rng.normal(size=n)
+    ctx = lb.Context(0).load(p)
+    Y = ctx.op_wsum_mulrk(0, wv, X, True)
+    assert rel(Y, orc.mul_rk(cone, orc.wsum(cone, wv, True), X)) < KTOL
+    ctx.close()
+    rho = 1.0 / np.sqrt(n)
+    R0 = rng.random((n, r)) - rng.random((n, r))
+    out = {}
+    for fused in (True, False):
+        ctx = lb.Context(0).load(p)
+        ctx.set_fused_path(fused)
+        ctx.alloc_vars([r], 2)
+        ctx.set_factor(lb.R, 0, R0)
+        ctx.init_constr_val(lb.PAIR_RR)
+        ctx.alm_cal_grad(rho)
+        hist = []
+        for it in range(12):
+            ctx.lbfgs_direction(it)
+            terms = ctx.alm_linesearch_terms(rho)
+            _, tau = _line_search(lb, rho, terms)
+            hist.append((tau,) + ctx.alm_inner_update(rho, tau))
+        out[fused] = (np.array(hist), ctx.get_factor(lb.R, 0), ctx.dual_infeasibility())
+        ctx.close()
+    assert np.all(np.abs(out[True][0] - out[False][0]) <= 1e-9 * np.abs(out[False][0]))
+    assert rel(out[True][1], out[False][1]) < 1e-10
+    assert abs(out[True][2] - out[False][2]) <= 1e-9 * (1.0 + abs(out[False][2]))
+
+
 def test_fused_path_tracks_general_path_at_c3_scale(lb):
     """A/B at the G81-like size (n = 20000, rank 20): 40 ALM inner iterations + dual update + 1 ADMM sweep on the
     fused MaxCut-type path and on the general path from the same start; trajectories must agree far inside the
