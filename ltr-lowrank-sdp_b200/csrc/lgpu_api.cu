@@ -343,6 +343,9 @@ static inline int pick_list_group(double avg_len)
     default: { constexpr int GG = 32; __VA_ARGS__; } break; \
     }
 
+static int run_long_rows(lgpu_ctx *ctx, DevCone &c, int64_t ld, const int32_t *slots, const double *vals, const double *Xin,
+                         const double *Xhalo, int nsplit, double alpha, double beta, const double *Z, double *T);
+
 /* UVt on the pattern of cone c from two row-major factors */
 static void run_uvt(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *U, const double *V, double *out)
 {
@@ -405,12 +408,7 @@ static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, con
     Prof pr(ctx, KC_SPMM);
     DISPATCH_G(G, k_spmm<GG><<<grid_for(ctx, c.n * GG, (const void *)k_spmm<GG>), LGPU_TPB, 0, ctx->stream>>>(
                       c.n, c.f_ptr, c.f_col, c.f_slot, S, X, (int)ld, alpha, beta, Z, Y));
-    if (c.n_long > 0) {
-        const int blocks = (int)std::min<int64_t>(c.n_long, (int64_t)ctx->num_sms * 4);
-        DISPATCH_G(G, k_spmm_long_rows<GG, false><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
-                          c.n_long, c.long_rows, c.f_ptr, c.f_col, c.f_slot, S, X, nullptr, 0, (int)ld, alpha, beta, Z, Y));
-        ctx->launches++;
-    }
+    run_long_rows(ctx, c, ld, c.f_slot, S, X, nullptr, 0, alpha, beta, Z, Y);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -525,7 +523,8 @@ static void free_cone(DevCone &c)
     dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid);
     dev_free(c.t_ptr); dev_free(c.t_loc); dev_free(c.t_gid); dev_free(c.t_val);
     dev_free(c.f_ptr); dev_free(c.f_col); dev_free(c.f_slot); dev_free(c.d_row); dev_free(c.d_val);
-    dev_free(c.long_rows); c.n_long = 0;
+    dev_free(c.long_rows); dev_free(c.long_first); dev_free(c.lw_row); dev_free(c.lw_beg); dev_free(c.lw_end);
+    dev_free(c.long_scratch); c.n_long = c.n_lwork = c.long_scratch_ld = 0;
     dev_free(c.mc_val); dev_free(c.rc_ptr); dev_free(c.rc_gid); dev_free(c.rc_a);
     dev_free(c.uvt); dev_free(c.S); dev_free(c.cv); dev_free(c.wtmp);
 }
@@ -692,15 +691,61 @@ static void cone_rules(int64_t n, int64_t m, const int64_t *beg, const int64_t *
     r.nnzP = r.dense ? tri : (int64_t)r.pat.size();
 }
 
-/* list of the CSR rows that k_spmm_long_rows takes over */
+/* work list of the CSR rows that k_spmm_long_chunks takes over */
 static int upload_long_rows(lgpu_ctx *ctx, DevCone &c, const std::vector<int32_t> &ptr)
 {
-    std::vector<int32_t> lr;
-    for (size_t i = 0; i + 1 < ptr.size(); ++i)
-        if (ptr[i + 1] - ptr[i] > LGPU_LONG_ROW) lr.push_back((int32_t)i);
+    std::vector<int32_t> lr, first(1, 0), wrow, wbeg, wend;
+    for (size_t i = 0; i + 1 < ptr.size(); ++i) {
+        if (ptr[i + 1] - ptr[i] <= LGPU_LONG_ROW) continue;
+        lr.push_back((int32_t)i);
+        for (int32_t e = ptr[i]; e < ptr[i + 1]; e += LGPU_LONG_CHUNK) {
+            wrow.push_back((int32_t)i);
+            wbeg.push_back(e);
+            wend.push_back(std::min<int32_t>(e + LGPU_LONG_CHUNK, ptr[i + 1]));
+        }
+        first.push_back((int32_t)wrow.size());
+    }
     c.n_long = (int64_t)lr.size();
-    dev_free(c.long_rows);
-    if (!lr.empty()) TRY(dev_upload(ctx, &c.long_rows, lr));
+    c.n_lwork = (int64_t)wrow.size();
+    dev_free(c.long_rows); dev_free(c.long_first); dev_free(c.lw_row); dev_free(c.lw_beg); dev_free(c.lw_end);
+    dev_free(c.long_scratch);
+    c.long_scratch_ld = 0;
+    if (!lr.empty()) {
+        TRY(dev_upload(ctx, &c.long_rows, lr));
+        TRY(dev_upload(ctx, &c.long_first, first));
+        TRY(dev_upload(ctx, &c.lw_row, wrow));
+        TRY(dev_upload(ctx, &c.lw_beg, wbeg));
+        TRY(dev_upload(ctx, &c.lw_end, wend));
+    }
+    return 0;
+}
+/* the long rows' share of  T = alpha S X + beta Z  (entry values vals[e], or vals[slots[e]]) */
+static int run_long_rows(lgpu_ctx *ctx, DevCone &c, int64_t ld, const int32_t *slots, const double *vals, const double *Xin,
+                         const double *Xhalo, int nsplit, double alpha, double beta, const double *Z, double *T)
+{
+    if (c.n_long == 0) return 0;
+    if (c.long_scratch_ld < ld) {
+        dev_free(c.long_scratch);
+        TRY(dev_alloc(ctx, &c.long_scratch, (size_t)c.n_lwork * (size_t)ld));
+        c.long_scratch_ld = ld;
+    }
+    const int G = pick_group(ld);
+    const int blocks = (int)std::min<int64_t>(c.n_lwork, (int64_t)ctx->num_sms * 8);
+    {
+        Prof pr(ctx, KC_SPMM);
+        if (Xhalo != nullptr) {
+            DISPATCH_G(G, k_spmm_long_chunks<GG, true><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
+                              c.n_lwork, c.lw_row, c.lw_beg, c.lw_end, c.f_col, slots, vals, Xin, Xhalo, nsplit, (int)ld, c.long_scratch));
+        } else {
+            DISPATCH_G(G, k_spmm_long_chunks<GG, false><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
+                              c.n_lwork, c.lw_row, c.lw_beg, c.lw_end, c.f_col, slots, vals, Xin, nullptr, 0, (int)ld, c.long_scratch));
+        }
+    }
+    {
+        Prof pr(ctx, KC_SPMM);
+        k_spmm_long_finish<<<grid_for(ctx, c.n_long * ld, (const void *)k_spmm_long_finish), LGPU_TPB, 0, ctx->stream>>>(
+            c.n_long, c.long_rows, c.long_first, (int)ld, c.long_scratch, alpha, beta, Z, T);
+    }
     return 0;
 }
 
@@ -1539,23 +1584,12 @@ static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
         const double *Xh = ctx->halo - (size_t)c.n_alloc * c.ld; /* halo row k is addressed as column n_alloc + k */
         DISPATCH_G(G, k_mc_spmm<GG, 2, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, true>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, c.f_ptr, c.f_col, c.mc_val, X, Xh, (int)c.n_alloc, (int)c.ld, T));
-        if (c.n_long > 0) {
-            const int blocks = (int)std::min<int64_t>(c.n_long, (int64_t)ctx->num_sms * 4);
-            DISPATCH_G(G, k_spmm_long_rows<GG, true><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
-                              c.n_long, c.long_rows, c.f_ptr, c.f_col, nullptr, c.mc_val, X, Xh, (int)c.n_alloc, (int)c.ld, 1.0, 0.0,
-                              nullptr, T));
-            ctx->launches++;
-        }
+        run_long_rows(ctx, c, c.ld, nullptr, c.mc_val, X, Xh, (int)c.n_alloc, 1.0, 0.0, nullptr, T);
     } else {
         const double *Xg = ctx->world > 1 ? ctx->gfull : X;
         DISPATCH_G(G, k_mc_spmm<GG, 2, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, false>), LGPU_TPB, 0, ctx->stream>>>(
                           c.n, c.f_ptr, c.f_col, c.mc_val, Xg, nullptr, 0, (int)c.ld, T));
-        if (c.n_long > 0) {
-            const int blocks = (int)std::min<int64_t>(c.n_long, (int64_t)ctx->num_sms * 4);
-            DISPATCH_G(G, k_spmm_long_rows<GG, false><<<blocks, LGPU_TPB, 0, ctx->stream>>>(
-                              c.n_long, c.long_rows, c.f_ptr, c.f_col, nullptr, c.mc_val, Xg, nullptr, 0, (int)c.ld, 1.0, 0.0, nullptr, T));
-            ctx->launches++;
-        }
+        run_long_rows(ctx, c, c.ld, nullptr, c.mc_val, Xg, nullptr, 0, 1.0, 0.0, nullptr, T);
     }
 }
 static void mc_refresh_cr(lgpu_ctx *ctx)

@@ -116,7 +116,10 @@ struct DevCone {
     int32_t *con_gid = nullptr;                  /* [mA] global constraint index */
     int32_t *t_ptr = nullptr, *t_loc = nullptr, *t_gid = nullptr; double *t_val = nullptr; /* by slot */
     int32_t *f_ptr = nullptr, *f_col = nullptr, *f_slot = nullptr; /* full CSR */
-    int32_t *long_rows = nullptr; int64_t n_long = 0;               /* rows with > LGPU_LONG_ROW entries */
+    /* rows with > LGPU_LONG_ROW entries, cut into chunks: work item w = entries [lw_beg, lw_end) of row lw_row */
+    int32_t *long_rows = nullptr, *long_first = nullptr; int64_t n_long = 0;
+    int32_t *lw_row = nullptr, *lw_beg = nullptr, *lw_end = nullptr; int64_t n_lwork = 0;
+    double *long_scratch = nullptr; int64_t long_scratch_ld = 0;
     int32_t *d_row = nullptr; double *d_val = nullptr; /* diag_only: row and value per constraint */
     /* diag_only fused path: C per full-CSR entry, and row -> constraints (global id, a_k) */
     double *mc_val = nullptr;

@@ -16,7 +16,8 @@
 #include "lgpu_internal.h"
 
 #define LGPU_TPB 256
-#define LGPU_LONG_ROW 96 /* CSR rows longer than this are processed by a whole CTA (k_spmm_long_rows) */
+#define LGPU_LONG_ROW 96    /* CSR rows longer than this leave the row-per-group kernels ...                  */
+#define LGPU_LONG_CHUNK 512 /* ... and are processed in chunks of this many entries, one CTA per chunk        */
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_spmm(int64_t n, const int32_t *__r
     const int ld2 = ld >> 1;
     for (int64_t i = g0; i < n; i += groups) {
         const int e0 = fptr[i], e1 = fptr[i + 1];
-        if (e1 - e0 > LGPU_LONG_ROW) continue; /* -> k_spmm_long_rows */
+        if (e1 - e0 > LGPU_LONG_ROW) continue; /* -> k_spmm_long_chunks */
         for (int cb = 0; cb < ld2; cb += G) {
             const int c = cb + lane;
             double2 acc = make_double2(0.0, 0.0);
@@ -565,7 +566,7 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
     const int ld2 = ld >> 1;
     for (int64_t i = g0; i < n; i += groups) {
         const int e0 = fptr[i], e1 = fptr[i + 1];
-        if (e1 - e0 > LGPU_LONG_ROW) continue; /* hub rows go to k_spmm_long_rows: one CTA per row */
+        if (e1 - e0 > LGPU_LONG_ROW) continue; /* hub rows go to k_spmm_long_chunks */
         for (int c = lane; c < ld2; c += G) {
             double2 acc = make_double2(0.0, 0.0);
             int e = e0;
@@ -593,26 +594,26 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
 #undef X_ROW
 }
 
-/* Rows of the symmetric CSR with more than LGPU_LONG_ROW entries (hub vertices, arrow-shaped patterns): one CTA per
- * row, its 256/G groups stride over the row's entries, partial sums meet in shared memory and are added in group
- * order (fixed order: bit-reproducible).  Without this a single group walks the whole row while the rest of the GPU
- * idles: ice_2.0 (n = 8113, one row of 8112 entries) spent 1.1 ms per product in it.
- * value of entry e: vals[e] (slots == nullptr) or vals[slots[e]] ; result alpha * sum + beta * Z */
+/* Rows of the symmetric CSR with more than LGPU_LONG_ROW entries (hub vertices, arrow-shaped patterns) are cut into
+ * chunks of LGPU_LONG_CHUNK entries; one CTA per chunk (its 256/G groups stride over the chunk, partial sums meet in
+ * shared memory in group order), partial rows go to scratch, and a second small kernel adds a row's chunks in chunk
+ * order and applies alpha/beta.  Fixed summation order: bit-reproducible.  Without this a single group walks the
+ * whole row while the rest of the GPU idles: ice_2.0 (n = 8113, one row of 8112 entries) spent 1.1 ms per product there.
+ * value of entry e: vals[e] (slots == nullptr) or vals[slots[e]] */
 template <int G, bool HALO>
-__global__ void __launch_bounds__(LGPU_TPB) k_spmm_long_rows(int64_t nlong, const int32_t *__restrict__ rows,
-                                                             const int32_t *__restrict__ fptr, const int32_t *__restrict__ fcol,
-                                                             const int32_t *__restrict__ slots, const double *__restrict__ vals,
-                                                             const double *__restrict__ Xin, const double *__restrict__ Xhalo,
-                                                             int nsplit, int ld, double alpha, double beta,
-                                                             const double *__restrict__ Z, double *__restrict__ T)
+__global__ void __launch_bounds__(LGPU_TPB) k_spmm_long_chunks(int64_t nwork, const int32_t *__restrict__ wrow,
+                                                               const int32_t *__restrict__ wbeg, const int32_t *__restrict__ wend,
+                                                               const int32_t *__restrict__ fcol, const int32_t *__restrict__ slots,
+                                                               const double *__restrict__ vals, const double *__restrict__ Xin,
+                                                               const double *__restrict__ Xhalo, int nsplit, int ld,
+                                                               double *__restrict__ scratch)
 {
     constexpr int NG = LGPU_TPB / G;
     __shared__ double2 part[NG][G];
     const int lane = threadIdx.x % G, grp = threadIdx.x / G;
     const int ld2 = ld >> 1;
-    for (int64_t k = blockIdx.x; k < nlong; k += gridDim.x) {
-        const int64_t i = rows[k];
-        const int e0 = fptr[i], e1 = fptr[i + 1];
+    for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int e0 = wbeg[w], e1 = wend[w];
         for (int cb = 0; cb < ld2; cb += G) {
             const int c = cb + lane;
             double2 acc = make_double2(0.0, 0.0);
@@ -629,15 +630,29 @@ __global__ void __launch_bounds__(LGPU_TPB) k_spmm_long_rows(int64_t nlong, cons
             if (grp == 0 && c < ld2) {
                 double2 t = part[0][lane];
                 for (int g = 1; g < NG; ++g) { t.x += part[g][lane].x; t.y += part[g][lane].y; }
-                double2 o = make_double2(alpha * t.x, alpha * t.y);
-                if (Z != nullptr) {
-                    const double2 z = reinterpret_cast<const double2 *>(Z + (size_t)i * ld)[c];
-                    o.x = fma(beta, z.x, o.x); o.y = fma(beta, z.y, o.y);
-                }
-                reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = o;
+                reinterpret_cast<double2 *>(scratch + (size_t)w * ld)[c] = t;
             }
             __syncthreads();
         }
+    }
+    (void)wrow;
+}
+__global__ void __launch_bounds__(LGPU_TPB) k_spmm_long_finish(int64_t nlong, const int32_t *__restrict__ rows,
+                                                               const int32_t *__restrict__ first, int ld,
+                                                               const double *__restrict__ scratch, double alpha, double beta,
+                                                               const double *__restrict__ Z, double *__restrict__ T)
+{
+    const int64_t total = nlong * (int64_t)ld;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+        const int64_t k = q / ld;
+        const int c = (int)(q - k * ld);
+        double t = 0.0;
+        for (int w = first[k]; w < first[k + 1]; ++w) t += scratch[(size_t)w * ld + c];
+        const size_t o = (size_t)rows[k] * ld + c;
+        double v = alpha * t;
+        if (Z != nullptr) v = fma(beta, Z[o], v);
+        T[o] = v;
     }
 }
 
