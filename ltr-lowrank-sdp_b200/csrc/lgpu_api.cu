@@ -369,10 +369,17 @@ static void run_uvt(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *U, cons
 static void run_con_gather(lgpu_ctx *ctx, DevCone &c, const double *uvt, double *cv)
 {
     if (c.mA == 0) return;
-    const int G = pick_list_group((double)c.nnzA / (double)c.mA);
-    Prof pr(ctx, KC_GATHER);
-    DISPATCH_G(G, k_con_gather<GG><<<grid_for(ctx, c.mA * GG), LGPU_TPB, 0, ctx->stream>>>(
-                      c.mA, c.a_ptr, c.a_slot, c.a_coef, uvt, cv));
+    const int G = c.con_group;
+    {
+        Prof pr(ctx, KC_GATHER);
+        DISPATCH_G(G, k_con_gather<GG><<<grid_for(ctx, c.mA * GG), LGPU_TPB, 0, ctx->stream>>>(
+                          c.mA, c.a_ptr, c.a_slot, c.a_coef, uvt, cv));
+    }
+    if (c.n_long_con > 0) {
+        Prof pr(ctx, KC_GATHER);
+        k_con_gather_long<<<(int)std::min<int64_t>(c.n_long_con, (int64_t)ctx->num_sms * 8), LGPU_TPB, 0, ctx->stream>>>(
+            c.n_long_con, c.long_con, c.a_ptr, c.a_slot, c.a_coef, uvt, cv);
+    }
 }
 /* <C, uvt> accumulated into dsc[slot] */
 static void run_obj_gather(lgpu_ctx *ctx, DevCone &c, const double *uvt, int slot, int accumulate)
@@ -520,7 +527,7 @@ extern "C" const char *lgpu_profile_class_name(int cls)
 static void free_cone(DevCone &c)
 {
     dev_free(c.pat_row); dev_free(c.pat_col); dev_free(c.cval); dev_free(c.c_slot); dev_free(c.c_coef);
-    dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid);
+    dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid); dev_free(c.long_con); c.n_long_con = 0;
     dev_free(c.t_ptr); dev_free(c.t_loc); dev_free(c.t_gid); dev_free(c.t_val);
     dev_free(c.f_ptr); dev_free(c.f_col); dev_free(c.f_slot); dev_free(c.d_row); dev_free(c.d_val);
     dev_free(c.long_rows); dev_free(c.long_first); dev_free(c.lw_row); dev_free(c.lw_beg); dev_free(c.lw_end);
@@ -1035,6 +1042,15 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     TRY(dev_upload(ctx, &c.a_slot, a_slot));
     TRY(dev_upload(ctx, &c.a_coef, a_coef));
     TRY(dev_upload(ctx, &c.con_gid, con_gid));
+    {
+        /* lane group of the per-constraint gather from the average list length; lists far above it get their own CTA */
+        c.con_group = pick_list_group(mA > 0 ? (double)c.nnzA / (double)mA : 0.0);
+        std::vector<int32_t> lc;
+        for (int64_t t = 0; t < mA; ++t)
+            if (a_ptr[t + 1] - a_ptr[t] > LGPU_LONG_ROW * c.con_group) lc.push_back((int32_t)t);
+        c.n_long_con = (int64_t)lc.size();
+        if (!lc.empty()) TRY(dev_upload(ctx, &c.long_con, lc));
+    }
     TRY(dev_upload(ctx, &c.t_ptr, t_ptr));
     TRY(dev_upload(ctx, &c.t_loc, t_loc));
     TRY(dev_upload(ctx, &c.t_gid, t_gid));

@@ -114,6 +114,7 @@ struct DevCone {
     int32_t *c_slot = nullptr; double *c_coef = nullptr; /* [nnzC] (2-delta) c */
     int32_t *a_ptr = nullptr, *a_slot = nullptr; double *a_coef = nullptr; /* CSR by constraint, coef=(2-delta)a */
     int32_t *con_gid = nullptr;                  /* [mA] global constraint index */
+    int32_t *long_con = nullptr; int64_t n_long_con = 0; int con_group = 1; /* constraints with outlier list lengths */
     int32_t *t_ptr = nullptr, *t_loc = nullptr, *t_gid = nullptr; double *t_val = nullptr; /* by slot */
     int32_t *f_ptr = nullptr, *f_col = nullptr, *f_slot = nullptr; /* full CSR */
     /* rows with > LGPU_LONG_ROW entries, cut into chunks: work item w = entries [lw_beg, lw_end) of row lw_row */

@@ -331,12 +331,40 @@ __global__ void __launch_bounds__(LGPU_TPB) k_con_gather(int64_t mA, const int32
         const int64_t t = g0 + it * groups;
         const bool live = t < mA;
         double a = 0.0;
+        bool mine = live;
         if (live) {
             const int e0 = aptr[t], e1 = aptr[t + 1];
-            for (int e = e0 + lane; e < e1; e += G) a = fma(acoef[e], uvt[aslot[e]], a);
+            if (e1 - e0 > LGPU_LONG_ROW * G) mine = false; /* a long list among short ones: k_con_gather_long */
+            else
+                for (int e = e0 + lane; e < e1; e += G) a = fma(acoef[e], uvt[aslot[e]], a);
         }
         a = group_sum<G>(a);
-        if (live && lane == 0) cv[t] = a;
+        if (mine && lane == 0) cv[t] = a;
+    }
+}
+
+/* constraints whose entry list is much longer than the rest (e.g. the trace constraint A = I of a theta problem among
+ * 37 466 single-entry ones): one CTA per constraint, fixed-order block sum.  A single thread walking such a list cost
+ * 109 us per launch on theta102. */
+__global__ void __launch_bounds__(LGPU_TPB) k_con_gather_long(int64_t nlong, const int32_t *__restrict__ which,
+                                                              const int32_t *__restrict__ aptr, const int32_t *__restrict__ aslot,
+                                                              const double *__restrict__ acoef, const double *__restrict__ uvt,
+                                                              double *__restrict__ cv)
+{
+    __shared__ double sh[LGPU_TPB / 32];
+    for (int64_t k = blockIdx.x; k < nlong; k += gridDim.x) {
+        const int t = which[k];
+        double a = 0.0;
+        for (int e = aptr[t] + threadIdx.x; e < aptr[t + 1]; e += LGPU_TPB) a = fma(acoef[e], uvt[aslot[e]], a);
+        a = warp_sum(a);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < LGPU_TPB / 32; ++w) s += sh[w];
+            cv[t] = s;
+        }
+        __syncthreads();
     }
 }
 
