@@ -2258,47 +2258,61 @@ static int cg_solve(lgpu_ctx *ctx, int ci, double *x, const double *fixed, const
     }
     CU(ctx, cudaMemcpyAsync(p, r, sizeof(double) * nr, cudaMemcpyDeviceToDevice, ctx->stream));
     int64_t it = 0;
+    bool have_beta = false; /* p <- beta p + r is pending (applied at the start of the next iteration) */
     for (int64_t k = 0; k < maxit; ++k) {
         it += 1;
-        cg_mvec(ctx, c, p, fixed, Q);
-        {
-            SlotSpec<2> sp;
-            sp.slot[0] = SC_CG_RR; sp.slot[1] = SC_CG_PQ; sp.accumulate = 0;
-            launch_reduce<2>(ctx, nr, [=] __device__(int64_t i, double(&acc)[2]) {
+        SlotSpec<2> sp;
+        sp.slot[0] = SC_CG_RR; sp.slot[1] = SC_CG_PQ; sp.accumulate = 0;
+        if (ctx->mc) {
+            /* fused: [p = beta p + r,] Q = M p, <r,r>, <p,Q>, alpha -- one launch */
+            const int G = pick_group(c.ld);
+            {
+                Prof pr(ctx, KC_MC_STEP);
+                DISPATCH_G(G, k_mc_cg_first<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_cg_first<GG>), LGPU_TPB, 0, ctx->stream>>>(
+                                  c.n, (int)c.ld, have_beta ? SC_CG_BETA : -1, p, r, fixed, c.rc_ptr, c.rc_a, Q, ctx->partials, ctx->counter,
+                                  ctx->dsc, sp, SC_CG_ALPHA));
+            }
+            if (ctx->world > 1) {
+                TRY(allreduce_scalars(ctx, SC_CG_RR, 2));
+                launch_scalar(ctx, [=] __device__() { dsc[SC_CG_ALPHA] = dsc[SC_CG_RR] / dsc[SC_CG_PQ]; });
+            }
+        } else {
+            if (have_beta) launch_map(ctx, nr, [=] __device__(int64_t i) { p[i] = fma(dsc[SC_CG_BETA], p[i], r[i]); });
+            cg_mvec(ctx, c, p, fixed, Q);
+            launch_reduce_post<2>(ctx, nr, [=] __device__(int64_t i, double(&acc)[2]) {
                 acc[0] = fma(r[i], r[i], acc[0]);
                 acc[1] = fma(p[i], Q[i], acc[1]);
-            }, sp);
+            }, sp, [=] __device__(double *sc) { sc[SC_CG_ALPHA] = sc[SC_CG_RR] / sc[SC_CG_PQ]; });
         }
-        launch_scalar(ctx, [=] __device__() { dsc[SC_CG_ALPHA] = dsc[SC_CG_RR] / dsc[SC_CG_PQ]; });
-        launch_reduce<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) {
+        /* x += alpha p ; r -= alpha Q ; <r,r> ; and, unless the residual is about to be recomputed, beta = <r,r>_new / <r,r>_old */
+        const bool restart = (k % 20 == 0);
+        auto upd = [=] __device__(int64_t i, double(&acc)[1]) {
             const double a = dsc[SC_CG_ALPHA];
             x[i] = fma(a, p[i], x[i]);
             const double v = fma(-a, Q[i], r[i]);
             r[i] = v;
             acc[0] = fma(v, v, acc[0]);
-        }, slot1(SC_CG_RES));
+        };
+        if (restart) launch_reduce_post<1>(ctx, nr, upd, slot1(SC_CG_RES), NoPost());
+        else launch_reduce_post<1>(ctx, nr, upd, slot1(SC_CG_RES), [=] __device__(double *sc) { sc[SC_CG_BETA] = sc[SC_CG_RES] / sc[SC_CG_RR]; });
         CHECK_LAUNCH(ctx);
         TRY(fetch_scalars(ctx, SC_CG_RES, 1));
         res = sqrt(ctx->hsc[SC_CG_RES]);
         if (res / bnorm < tol) break;
-        if (k % 20 == 0) {
-            /* residual recomputed from scratch, p = q = r (lorads_cgs.c:242-258); the update below then runs with
-             * beta = 1, i.e. p = 2 r -- reproduced as is */
+        if (restart) {
+            /* residual recomputed from scratch, p = q = r (lorads_cgs.c:242-258); the update that follows runs with
+             * beta = <r,r>/<r,r> = 1, i.e. p = 2 r -- reproduced as is */
             cg_mvec(ctx, c, x, fixed, r);
-            launch_reduce<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) {
+            launch_reduce_post<1>(ctx, nr, [=] __device__(int64_t i, double(&acc)[1]) {
                 const double v = bvec[i] - r[i];
                 r[i] = v;
                 p[i] = v;
                 acc[0] = fma(v, v, acc[0]);
-            }, slot1(SC_CG_RR));
-            /* qTrNew = r.r = qTr -> beta = qTrNew / qTr (1 unless r.r is 0/NaN) */
-            launch_scalar(ctx, [=] __device__() { dsc[SC_CG_BETA] = dsc[SC_CG_RR] / dsc[SC_CG_RR]; });
-        } else {
-            /* beta = (r_new . r_new) / (r_old . r_old): numerator is SC_CG_RES, denominator SC_CG_RR */
-            launch_scalar(ctx, [=] __device__() { dsc[SC_CG_BETA] = dsc[SC_CG_RES] / dsc[SC_CG_RR]; });
+            }, slot1(SC_CG_RR), [=] __device__(double *sc) { sc[SC_CG_BETA] = sc[SC_CG_RR] / sc[SC_CG_RR]; });
         }
-        launch_map(ctx, nr, [=] __device__(int64_t i) { p[i] = fma(dsc[SC_CG_BETA], p[i], r[i]); });
+        have_beta = true;
     }
+    /* (the reference also forms p = beta p + r after its last iteration; p is scratch there, nothing reads it again) */
     ctx->cg_last_iter[ci] = it;
     *iters = it;
     return 0;

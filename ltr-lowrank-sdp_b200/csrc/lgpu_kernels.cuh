@@ -684,6 +684,58 @@ __global__ void __launch_bounds__(LGPU_TPB) k_spmm_long_finish(int64_t nlong, co
     }
 }
 
+/* One CG iteration's first half for diagonal constraints, fused (lorads_cgs.c:209-236 with linSysProduct,
+ * lorads_admm.c:471-486): [p = beta p + r ;]  Q = p + Diag(c_i <p_i, V_i>) V ;  sums <r, r> and <p, Q> ; the finishing
+ * thread forms alpha = <r,r> / <p,Q>.  beta is read from dsc[beta_slot] (beta_slot < 0: p is used as it is). */
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_mc_cg_first(int64_t n, int ld, int beta_slot, double *__restrict__ P,
+                                                          const double *__restrict__ Rr, const double *__restrict__ Vf,
+                                                          const int32_t *__restrict__ rcptr, const double *__restrict__ rca,
+                                                          double *__restrict__ Q, double *partials, unsigned int *counter,
+                                                          double *dsc, SlotSpec<2> spec, int alpha_slot)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    const int64_t iters = (n + groups - 1) / groups;
+    const double beta = beta_slot >= 0 ? dsc[beta_slot] : 0.0;
+    double red[2] = {0.0, 0.0};
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = g0 + it * groups;
+        const bool live = i < n;
+        double pv = 0.0;
+        if (live)
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                double2 p = reinterpret_cast<double2 *>(P)[w];
+                const double2 r = reinterpret_cast<const double2 *>(Rr)[w];
+                if (beta_slot >= 0) {
+                    p.x = fma(beta, p.x, r.x); p.y = fma(beta, p.y, r.y);
+                    reinterpret_cast<double2 *>(P)[w] = p;
+                }
+                const double2 v = reinterpret_cast<const double2 *>(Vf)[w];
+                pv = fma(p.x, v.x, pv); pv = fma(p.y, v.y, pv);
+                red[0] = fma(r.x, r.x, red[0]); red[0] = fma(r.y, r.y, red[0]);
+            }
+        pv = group_sum<G>(pv);
+        if (live) {
+            double dg = 0.0;
+            for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) dg = fma(rca[t] * pv, rca[t], dg);
+            for (int c = lane; c < ld2; c += G) {
+                const size_t w = (size_t)i * ld2 + c;
+                const double2 p = reinterpret_cast<const double2 *>(P)[w];
+                const double2 v = reinterpret_cast<const double2 *>(Vf)[w];
+                const double2 q = make_double2(fma(dg, v.x, p.x), fma(dg, v.y, p.y));
+                reinterpret_cast<double2 *>(Q)[w] = q;
+                red[1] = fma(p.x, q.x, red[1]); red[1] = fma(p.y, q.y, red[1]);
+            }
+        }
+    }
+    const int rr = spec.slot[0], pq = spec.slot[1];
+    grid_reduce_finish<2>(red, partials, counter, dsc, spec, [=] __device__(double *sc) { sc[alpha_slot] = sc[rr] / sc[pq]; });
+}
+
 /* pack the rows other ranks need into the send buffer (grouped by destination): out[k] = X[idx[k]] */
 template <int G>
 __global__ void __launch_bounds__(LGPU_TPB) k_pack_rows(int64_t nrows, int ld, const int32_t *__restrict__ idx,

@@ -52,7 +52,7 @@ def stage():
 def parse(out):
     res = {}
     for line in out.splitlines():
-        if line.startswith("ALM OuterIter:"):
+        if "OuterIter:" in line and "InnerIter:" in line:   # the 64-bit reference build prints no "ALM " prefix
             res["alm_inner_iters"] = int(line.split("InnerIter:")[1].split()[0])
             res["rank"] = int(line.split("CurrRank:")[1].split()[0])
         elif line.startswith("ADMM Iter:"):
