@@ -403,12 +403,34 @@ static void run_spmm(lgpu_ctx *ctx, DevCone &c, int64_t ld, const double *S, con
                      const double *Z, double *Y)
 {
     if (c.dense_aggregate && ctx->dense_dmma) {
-        const int64_t ntiles = ((c.n + 7) / 8) * ((ld + 63) / 64);
+        /* enough warps to fill the GPU: (row tiles) x (column tiles) x (k ranges), k split in multiples of 4 */
+        const int64_t base = ((c.n + 7) / 8) * ((ld + 7) / 8);
+        int ksplit = 1;
+        while (ksplit < 16 && base * ksplit < (int64_t)ctx->num_sms * 32 && c.n / (ksplit * 2) >= 64) ksplit *= 2;
+        const int64_t klen = (((c.n + ksplit - 1) / ksplit) + 3) / 4 * 4;
+        const int64_t ntiles = base * ksplit;
         int64_t blocks = (ntiles + 3) / 4;
-        const int64_t cap = (int64_t)ctx->num_sms * 8;
+        const int64_t cap = (int64_t)ctx->num_sms * 16;
         if (blocks > cap) blocks = cap;
-        Prof pr(ctx, KC_DENSE);
-        k_dense_symm<<<(unsigned)blocks, 128, 0, ctx->stream>>>(c.n, (int)ld, S, X, alpha, beta, Z, Y);
+        double *scratch = nullptr;
+        if (ksplit > 1) {
+            const int64_t need = (int64_t)ksplit * c.n * ld;
+            if (c.symm_scratch_len < need) {
+                dev_free(c.symm_scratch);
+                if (dev_alloc(ctx, &c.symm_scratch, (size_t)need) != 0) return;
+                c.symm_scratch_len = need;
+            }
+            scratch = c.symm_scratch;
+        }
+        {
+            Prof pr(ctx, KC_DENSE);
+            k_dense_symm<<<(unsigned)blocks, 128, 0, ctx->stream>>>(c.n, (int)ld, ksplit, klen, S, X, alpha, beta, Z, Y, scratch);
+        }
+        if (ksplit > 1) {
+            Prof pr(ctx, KC_DENSE);
+            k_dense_symm_finish<<<grid_for(ctx, c.n * ld, (const void *)k_dense_symm_finish), LGPU_TPB, 0, ctx->stream>>>(
+                c.n * ld, c.n * ld, ksplit, scratch, alpha, beta, Z, Y);
+        }
         return;
     }
     const int G = pick_group(ld);
@@ -532,6 +554,7 @@ static void free_cone(DevCone &c)
     dev_free(c.f_ptr); dev_free(c.f_col); dev_free(c.f_slot); dev_free(c.d_row); dev_free(c.d_val);
     dev_free(c.long_rows); dev_free(c.long_first); dev_free(c.lw_row); dev_free(c.lw_beg); dev_free(c.lw_end);
     dev_free(c.long_scratch); c.n_long = c.n_lwork = c.long_scratch_ld = 0;
+    dev_free(c.symm_scratch); c.symm_scratch_len = 0;
     dev_free(c.mc_val); dev_free(c.rc_ptr); dev_free(c.rc_gid); dev_free(c.rc_a);
     dev_free(c.uvt); dev_free(c.S); dev_free(c.cv); dev_free(c.wtmp);
 }

@@ -121,6 +121,7 @@ struct DevCone {
     int32_t *long_rows = nullptr, *long_first = nullptr; int64_t n_long = 0;
     int32_t *lw_row = nullptr, *lw_beg = nullptr, *lw_end = nullptr; int64_t n_lwork = 0;
     double *long_scratch = nullptr; int64_t long_scratch_ld = 0;
+    double *symm_scratch = nullptr; int64_t symm_scratch_len = 0; /* split-k partials of the dense SYMM */
     int32_t *d_row = nullptr; double *d_val = nullptr; /* diag_only: row and value per constraint */
     /* diag_only fused path: C per full-CSR entry, and row -> constraints (global id, a_k) */
     double *mc_val = nullptr;

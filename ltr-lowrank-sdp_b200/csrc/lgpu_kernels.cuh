@@ -267,47 +267,68 @@ __global__ void __launch_bounds__(128) k_dense_uvt(int64_t n, int ld, const doub
 
 /* K4d  Y = alpha S X + beta Z, S dense symmetric given on the packed lower triangle (never unpacked to n x n)
  *      reference: dataMatDenseMultiRkMat (unpack + dsymm on every call), lorads_sdp_data.c:948-973
- * One warp per 8 rows x 64 columns of Y; the S fragment of a k-step is reused by the 8 column tiles. */
-__global__ void __launch_bounds__(128) k_dense_symm(int64_t n, int ld, const double *__restrict__ S,
+ * One warp per (8-row tile, 8-column tile, k-range): the block dimension n is small (hundreds to a few thousand), so
+ * the parallelism has to come from the column tiles and from splitting the k loop -- the first version (one warp per
+ * 8 rows x 64 columns, whole k loop) ran 94 CTAs at 6 % warps active on n = 3000.  Column tiles vary fastest, so the
+ * warps of a CTA share the S fragment through L1.  ksplit > 1: raw partial sums go to scratch[ks][n][ld] and
+ * k_dense_symm_finish adds them in k order (fixed order) and applies alpha / beta. */
+__global__ void __launch_bounds__(128) k_dense_symm(int64_t n, int ld, int ksplit, int64_t klen, const double *__restrict__ S,
                                                     const double *__restrict__ X, double alpha, double beta,
-                                                    const double *__restrict__ Z, double *__restrict__ Y)
+                                                    const double *__restrict__ Z, double *__restrict__ Y,
+                                                    double *__restrict__ scratch)
 {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int64_t rt = (n + 7) / 8;
-    const int ct = (ld + 63) / 64;
-    const int64_t ntiles = rt * ct;
+    const int ct = (ld + 7) / 8;
+    const int64_t ntiles = rt * ct * ksplit;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t w = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < ntiles; w += warps) {
-        const int64_t i0 = (w / ct) * 8;
-        const int c0 = (int)(w % ct) * 64;
+        const int c0 = (int)(w % ct) * 8;
+        const int64_t rest = w / ct;
+        const int64_t i0 = (rest % rt) * 8;
+        const int ks = (int)(rest / rt);
+        const int64_t kbeg = (int64_t)ks * klen, kend = (kbeg + klen < n) ? kbeg + klen : n;
         const int64_t i = i0 + g;
-        double acc[8][2];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = 0.0;
-        for (int64_t k0 = 0; k0 < n; k0 += 4) {
+        const int colb = c0 + g;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int64_t k0 = kbeg; k0 < kend; k0 += 4) {
             const int64_t k = k0 + t;
-            double a = 0.0;
-            if (i < n && k < n) a = (i >= k) ? S[(2 * n - k - 1) * k / 2 + i] : S[(2 * n - i - 1) * i / 2 + k];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int col = c0 + q * 8 + g;
-                const double b = (k < n && col < ld) ? X[(size_t)k * ld + col] : 0.0;
-                dmma_m8n8k4(acc[q][0], acc[q][1], a, b);
+            double a = 0.0, b = 0.0;
+            if (k < kend) {
+                if (i < n) a = (i >= k) ? S[(2 * n - k - 1) * k / 2 + i] : S[(2 * n - i - 1) * i / 2 + k];
+                if (colb < ld) b = X[(size_t)k * ld + colb];
             }
+            dmma_m8n8k4(acc0, acc1, a, b);
         }
         if (i < n) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = c0 + q * 8 + 2 * t + e;
-                    if (col < ld) {
-                        double o = alpha * acc[q][e];
+            for (int e = 0; e < 2; ++e) {
+                const int col = c0 + 2 * t + e;
+                if (col < ld) {
+                    const double v = e ? acc1 : acc0;
+                    if (ksplit > 1) {
+                        scratch[((size_t)ks * n + i) * ld + col] = v;
+                    } else {
+                        double o = alpha * v;
                         if (Z != nullptr) o = fma(beta, Z[(size_t)i * ld + col], o);
                         Y[(size_t)i * ld + col] = o;
                     }
                 }
+            }
         }
+    }
+}
+__global__ void __launch_bounds__(LGPU_TPB) k_dense_symm_finish(int64_t total, int64_t nld, int ksplit,
+                                                                const double *__restrict__ scratch, double alpha, double beta,
+                                                                const double *__restrict__ Z, double *__restrict__ Y)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+        double tsum = 0.0;
+        for (int ks = 0; ks < ksplit; ++ks) tsum += scratch[(size_t)ks * nld + q];
+        double o = alpha * tsum;
+        if (Z != nullptr) o = fma(beta, Z[q], o);
+        Y[q] = o;
     }
 }
 
