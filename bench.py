@@ -376,6 +376,17 @@ def run_ours(args):
             "ms_per_launch": per_launch_ms, "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": None,
             "classes": {kname: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                         for kname, v in prof.items() if v[1]}}
+    # DRAM bytes of that kernel from the committed `ncu --set full` capture (same workload only)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            cap = json.load(f)
+        wl = cap["workload"]
+        if wl["n"] == n and wl["rank"] == r and wl["n_gpus"] == world and dom[0] in cap["kernels"]:
+            kk = cap["kernels"][dom[0]]
+            roof["traffic"] = kk["dram_read_bytes"] + kk["dram_write_bytes"]
+            roof["traffic_source"] = cap["source"]
+    except Exception:
+        pass
     if ab is not None:
         roof["algorithmic_bytes_per_launch"] = ab
         roof["achieved"] = ab / (per_launch_ms * 1e-3) / 1e9
