@@ -295,7 +295,10 @@ int lorads_b200_main(int argc, char **argv)
             S->scheduleLen = 0;
         }
     }
+    printf("Pre-solver starts \n");       /* LORADSPreprocess prints these three lines (lorads_solver.c:284-290) */
+    printf("  Processing the cones \n");
     if (lh_setup_problem(S, &data, &params) != LH_RET_OK) { exit_code = 3; goto cleanup; }
+    printf("  End preprocess \n");
     const int want_profile = getenv("LORADS_PROFILE") != NULL; /* per-kernel-class device time, printed at the end */
     if (want_profile) lgpu_profile_enable(S->gpu, 1);
     lh_determine_rank(S, &params);
@@ -419,7 +422,7 @@ end_solving: {
     printf("all_time - all_dual_infea: %f\n", all_time - all_dual_infea);
     printf("all_dual_infea: %f\n", all_dual_infea);
     printf("all_time: %f\n", all_time);
-    printf("gpu kernel launches: %lld\n", (long long)lgpu_launch_count(S->gpu));
+    fprintf(stderr, "lorads_b200: %lld kernel launches\n", (long long)lgpu_launch_count(S->gpu)); /* stdout stays the reference's */
     if (want_profile) {
         double ms[32];
         int64_t cnt[32];
