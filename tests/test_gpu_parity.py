@@ -369,6 +369,41 @@ def test_hub_rows_long_row_kernel(lb, tmp_path):
     assert abs(out[True][2] - out[False][2]) <= 1e-9 * (1.0 + abs(out[False][2]))
 
 
+@pytest.mark.parametrize("r", [1, 3, 9, 33, 70])
+def test_fused_path_rank_extremes(lb, r):
+    """lane-group sizes 4..32 and the multi-word loop (rank > 64): fused MaxCut-type path vs general path, 8 iterations"""
+    n = 1500
+    ei, ej, w = lb.random_graph(n, 4, 7)
+    rng = np.random.default_rng(r)
+    w = rng.choice([-1.0, 1.0], size=len(ei))
+    p = lb.maxcut_problem(n, ei, ej, w)
+    R0 = rng.random((n, r)) - rng.random((n, r))
+    rho = 1.0 / np.sqrt(n)
+    out = {}
+    for fused in (True, False):
+        ctx = lb.Context(0).load(p)
+        ctx.set_fused_path(fused)
+        ctx.alloc_vars([r], 2)
+        ctx.set_factor(lb.R, 0, R0)
+        ctx.init_constr_val(lb.PAIR_RR)
+        ctx.alm_cal_grad(rho)
+        hist = []
+        for it in range(8):
+            ctx.lbfgs_direction(it)
+            terms = ctx.alm_linesearch_terms(rho)
+            _, tau = _line_search(lb, rho, terms)
+            hist.append((tau,) + ctx.alm_inner_update(rho, tau))
+        ctx.alm_to_admm()
+        ctx.init_constr_val(lb.PAIR_UV)
+        cg = ctx.admm_update_var(10 * rho, 1e-6, 800, 0)
+        out[fused] = (np.array(hist), ctx.get_factor(lb.R, 0), cg, ctx.get_factor(lb.U, 0))
+        ctx.close()
+    assert np.all(np.abs(out[True][0] - out[False][0]) <= 1e-9 * np.abs(out[False][0]))
+    assert rel(out[True][1], out[False][1]) < 1e-10
+    assert abs(out[True][2] - out[False][2]) <= max(2, 0.05 * out[False][2])
+    assert rel(out[True][3], out[False][3]) < 1e-4
+
+
 def test_fused_path_tracks_general_path_at_c3_scale(lb):
     """A/B at the G81-like size (n = 20000, rank 20): 40 ALM inner iterations + dual update + 1 ADMM sweep on the
     fused MaxCut-type path and on the general path from the same start; trajectories must agree far inside the
