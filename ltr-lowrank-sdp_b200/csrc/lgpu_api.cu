@@ -2413,47 +2413,15 @@ static void refresh_cone_cv(lgpu_ctx *ctx, DevCone &c)
     launch_map(ctx, c.mA, [=] __device__(int64_t t) { cvs[gid[t]] += cv[t]; });
 }
 
-/* LORADSUpdateLPVarOne sweep on the host (lorads_admm.c:759-792, lorads_alg_common.c:356-374): the LP block is a
- * strictly sequential Gauss-Seidel over scalar columns; it works on host copies of the m-vectors. */
+/* LORADSUpdateLPVarOne sweep (lorads_admm.c:759-792, lorads_alg_common.c:356-374): strictly sequential over the LP
+ * columns; one warp on the device, state stays in HBM */
 static int admm_lp_sweep(lgpu_ctx *ctx, double rho)
 {
     DevLp &lp = ctx->lp;
-    const int64_t m = ctx->m, n = lp.n;
-    std::vector<double> cvs(m), lam(m), u(n), v(n);
-    CU(ctx, cudaMemcpyAsync(cvs.data(), ctx->cvs, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(lam.data(), ctx->lam, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(u.data(), ctx->U + lp.off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(v.data(), ctx->V + lp.off, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    const std::vector<double> &b = ctx->h_b;
-    for (int64_t j = 0; j < n; ++j) {
-        const int32_t e0 = lp.h_c_ptr[j], e1 = lp.h_c_ptr[j + 1];
-        for (int pass = 0; pass < 2; ++pass) {
-            double *upd = pass == 0 ? &u[j] : &v[j];
-            const double fixed = pass == 0 ? v[j] : u[j];
-            const double uv_old = u[j] * v[j];
-            double w = lp.h_obj[j];
-            for (int32_t e = e0; e < e1; ++e) {
-                const int32_t i = lp.h_c_row[e];
-                const double m1 = rho * (-b[i] + cvs[i] - lp.h_c_val[e] * uv_old) - lam[i];
-                w += m1 * lp.h_c_val[e];
-            }
-            double M2 = w * fixed;
-            M2 = M2 - rho * fixed;
-            const double blin = -1.0 * M2 / rho;
-            *upd = blin / (1 + lp.h_nrm2sq[j] * fixed * fixed);
-            const double uv_new = u[j] * v[j];
-            for (int32_t e = e0; e < e1; ++e) {
-                const int32_t i = lp.h_c_row[e];
-                cvs[i] -= lp.h_c_val[e] * uv_old;
-                cvs[i] += lp.h_c_val[e] * uv_new;
-            }
-        }
-    }
-    CU(ctx, cudaMemcpyAsync(ctx->cvs, cvs.data(), sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(ctx->U + lp.off, u.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(ctx->V + lp.off, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    Prof pr(ctx, KC_VEC);
+    k_lp_admm_sweep<<<1, 32, 0, ctx->stream>>>(lp.n, rho, lp.c_ptr, lp.c_row, lp.c_val, lp.obj, lp.nrm2sq, ctx->b, ctx->lam, ctx->cvs,
+                                               ctx->U + lp.off, ctx->V + lp.off);
+    CHECK_LAUNCH(ctx);
     return 0;
 }
 
@@ -2628,17 +2596,19 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
     if (ctx->world > 1) LGPU_FAIL(ctx, "dual infeasibility is not partitioned in this build (run it on one GPU)");
     double total = 0.0;
     /* LP part (lorads_solver.c:1404-1412): |min(c_j - a_j^T lambda, 0)| */
-    if (ctx->lp.n > 0) {
-        std::vector<double> lam(ctx->m);
-        CU(ctx, cudaMemcpyAsync(lam.data(), ctx->lam, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int64_t j = 0; j < ctx->lp.n; ++j) {
-            double w = ctx->lp.h_obj[j];
-            for (int32_t e = ctx->lp.h_c_ptr[j]; e < ctx->lp.h_c_ptr[j + 1]; ++e) w += -lam[ctx->lp.h_c_row[e]] * ctx->lp.h_c_val[e];
-            total += fabs(std::min(w, 0.0));
-        }
-    }
     double *dsc = ctx->dsc;
+    if (ctx->lp.n > 0) {
+        const int32_t *cp = ctx->lp.c_ptr, *cr = ctx->lp.c_row;
+        const double *cv = ctx->lp.c_val, *obj = ctx->lp.obj, *lam = ctx->lam;
+        launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) {
+            double w = obj[j];
+            for (int e = cp[j]; e < cp[j + 1]; ++e) w = fma(-lam[cr[e]], cv[e], w);
+            acc[0] += fabs(fmin(w, 0.0));
+        }, slot1(SC_LANCZOS + 2));
+        CHECK_LAUNCH(ctx);
+        TRY(fetch_scalars(ctx, SC_LANCZOS + 2, 1));
+        total += ctx->hsc[SC_LANCZOS + 2];
+    }
     for (auto &c : ctx->cones) {
         const int64_t n = c.n;
         const int kmax = (int)std::min<int64_t>(n, 300);

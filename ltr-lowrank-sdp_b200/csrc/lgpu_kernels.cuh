@@ -757,6 +757,54 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_cg_first(int64_t n, int ld, int
     grid_reduce_finish<2>(red, partials, counter, dsc, spec, [=] __device__(double *sc) { sc[alpha_slot] = sc[rr] / sc[pq]; });
 }
 
+/* ADMM update of the LP block: LORADSUpdateLPVarOne over the columns, u_j then v_j, constrValSum refreshed after every
+ * single update (lorads_admm.c:759-792, lorads_alg_common.c:356-374).  The sweep is a Gauss-Seidel recurrence through
+ * constrValSum, sequential by construction, so it runs as ONE warp that walks the columns in order; the lanes share a
+ * column's entries (a column touches distinct constraints, so its constrValSum updates do not collide). */
+__global__ void __launch_bounds__(32) k_lp_admm_sweep(int64_t nlp, double rho, const int32_t *__restrict__ cptr,
+                                                      const int32_t *__restrict__ crow, const double *__restrict__ cval,
+                                                      const double *__restrict__ obj, const double *__restrict__ nrm2sq,
+                                                      const double *__restrict__ b, const double *__restrict__ lam,
+                                                      double *cvs, double *u, double *v)
+{
+    const int lane = threadIdx.x;
+    for (int64_t j = 0; j < nlp; ++j) {
+        const int e0 = cptr[j], e1 = cptr[j + 1];
+        for (int pass = 0; pass < 2; ++pass) {
+            const double uj = ((volatile double *)u)[j], vj = ((volatile double *)v)[j];
+            const double fixed = pass == 0 ? vj : uj;
+            const double uv_old = uj * vj;
+            double part = 0.0;
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const int i = crow[e];
+                const double a = cval[e];
+                const double m1 = rho * (-b[i] + ((volatile double *)cvs)[i] - a * uv_old) - lam[i];
+                part = fma(m1, a, part);
+            }
+            const double w = obj[j] + warp_sum(part);
+            double M2 = w * fixed;
+            M2 = M2 - rho * fixed;
+            const double blin = -1.0 * M2 / rho;
+            const double nv = blin / (1 + nrm2sq[j] * fixed * fixed);
+            const double uv_new = pass == 0 ? nv * vj : uj * nv;
+            if (lane == 0) {
+                if (pass == 0) u[j] = nv;
+                else v[j] = nv;
+            }
+            for (int e = e0 + lane; e < e1; e += 32) {
+                const int i = crow[e];
+                const double a = cval[e];
+                double c = ((volatile double *)cvs)[i];
+                c -= a * uv_old;
+                c += a * uv_new;
+                cvs[i] = c;
+            }
+            __threadfence_block();
+            __syncwarp();
+        }
+    }
+}
+
 /* pack the rows other ranks need into the send buffer (grouped by destination): out[k] = X[idx[k]] */
 template <int G>
 __global__ void __launch_bounds__(LGPU_TPB) k_pack_rows(int64_t nrows, int ld, const int32_t *__restrict__ idx,
