@@ -1674,6 +1674,12 @@ static void cones_auv(lgpu_ctx *ctx, const double *A, const double *B, int obj_s
 static void sum_constr_vals(lgpu_ctx *ctx, const double *A, const double *B, double scale, double *out)
 {
     const int64_t m = ctx->m;
+    if (ctx->lp.n == 0 && ctx->ncones == 1 && ctx->cones[0].mA == m) {
+        /* one cone in which every constraint is non-zero: its compact constrVal IS the m-vector (con_gid = identity) */
+        const double *cv = ctx->cones[0].cv;
+        launch_map(ctx, m, [=] __device__(int64_t i) { out[i] = 0.0 + scale * cv[i]; });
+        return;
+    }
     if (ctx->lp.n > 0) {
         const int32_t *rp = ctx->lp.r_ptr, *rc = ctx->lp.r_col;
         const double *rv = ctx->lp.r_val;
@@ -2021,16 +2027,14 @@ extern "C" int lgpu_lbfgs_push(lgpu_ctx *ctx, double tau)
     CU(ctx, cudaSetDevice(ctx->device));
     double *sh = ctx->s[ctx->head], *yh = ctx->y[ctx->head];
     const double *G = ctx->G, *D = ctx->U;
-    double *dsc = ctx->dsc;
-    launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) {
+    const int ib = SC_BETA0 + ctx->head;
+    launch_reduce_post<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) {
         const double sv = tau * D[i];
         const double yv = yh[i] + G[i];
         sh[i] = sv;
         yh[i] = yv;
         acc[0] = fma(yv, sv, acc[0]);
-    }, slot1(SC_YS));
-    const int ib = SC_BETA0 + ctx->head;
-    launch_scalar(ctx, [=] __device__() { dsc[ib] = 1.0 / dsc[SC_YS]; });
+    }, slot1(SC_YS), [=] __device__(double *sc) { sc[ib] = 1.0 / sc[SC_YS]; });
     ctx->gram_pair_ok[ctx->head] = false;
     ctx->head = (ctx->head + 1) % ctx->h;
     ctx->gram_valid = false;
