@@ -41,6 +41,9 @@ typedef struct {
     /* B200 additions */
     int device;
     int quiet;
+    /* row-block partitioned run: `ranks` processes (one per GPU) forked by the driver, this one is `rank` */
+    int ranks, rank;
+    unsigned char ncclId[128];
 } lh_params;
 
 /* ---- SDPA data exactly as the reference reader hands it on (LReadSDPA, lorads_file_io.c:59) ----*/

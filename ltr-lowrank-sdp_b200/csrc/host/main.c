@@ -10,7 +10,10 @@
  *   --rankSchedule <json>   {"rank_schedule":[...], "schedule_length":N}  (benchmark.py:123-133)
  *   --nearStallFactor <f>   scales the ALM stall counter threshold that triggers a rank change
  *   --disableOracle         skip the per-iteration oracle-rank eigen-decomposition (reported as 0)
- * and `--device <id>` to choose the GPU.
+ * `--device <id>` to choose the GPU, and `--ranks <P>` for a row-block partitioned run on P GPUs of this node: the
+ * driver forks P processes (one per GPU, devices id .. id+P-1) BEFORE anything touches CUDA, rank 0 creates the NCCL id
+ * and hands it to the others through pipes, every rank runs the same state machine on the same reduced scalars, and
+ * only rank 0 prints and writes the log / JSON.
  */
 #include <ctype.h>
 #include <getopt.h>
@@ -18,6 +21,8 @@
 #include <signal.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include "lorads_host.h"
 
@@ -86,6 +91,7 @@ static struct option long_options[] = {
     {"nearStallFactor", required_argument, 0, 2001},
     {"disableOracle", no_argument, 0, 2002},
     {"device", required_argument, 0, 2003},
+    {"ranks", required_argument, 0, 2004},
     {0, 0, 0, 0}};
 
 static void print_input(const lh_params *p)
@@ -259,10 +265,55 @@ int lorads_b200_main(int argc, char **argv)
         case 2001: params.nearStallFactor = atof(optarg); break;
         case 2002: params.disableOracle = 1; break;
         case 2003: params.device = atoi(optarg); break;
+        case 2004: params.ranks = atoi(optarg); break;
         default: break;
         }
     }
     params.rhoCellingADMM = params.rhoMax * 200;
+
+    /* ---- fork the ranks of a partitioned run (no CUDA call has happened yet) --------------------------------*/
+    pid_t kids[64];
+    int nkids = 0;
+    if (params.ranks > 64) params.ranks = 64;
+    if (params.ranks > 1) {
+        int fds[64][2];
+        for (int r = 1; r < params.ranks; ++r)
+            if (pipe(fds[r]) != 0) { perror("pipe"); return 3; }
+        fflush(stdout);
+        for (int r = 1; r < params.ranks; ++r) {
+            const pid_t pid = fork();
+            if (pid < 0) { perror("fork"); return 3; }
+            if (pid == 0) { /* child: rank r */
+                params.rank = r;
+                nkids = 0;
+                for (int q = 1; q < params.ranks; ++q) {
+                    close(fds[q][1]);
+                    if (q != r) close(fds[q][0]);
+                }
+                size_t got = 0;
+                while (got < sizeof(params.ncclId)) {
+                    const ssize_t k = read(fds[r][0], params.ncclId + got, sizeof(params.ncclId) - got);
+                    if (k <= 0) { fprintf(stderr, "lorads_b200: rank %d did not receive the communicator id\n", r); return 3; }
+                    got += (size_t)k;
+                }
+                close(fds[r][0]);
+                if (!freopen("/dev/null", "w", stdout)) return 3; /* only rank 0 prints */
+                params.logFile = NULL;
+                params.jsonFile = NULL;
+                break;
+            }
+            kids[nkids++] = pid;
+        }
+        if (params.rank == 0) {
+            if (lgpu_nccl_unique_id(params.ncclId) != 0) { fprintf(stderr, "lorads_b200: cannot create the NCCL id\n"); return 3; }
+            for (int r = 1; r < params.ranks; ++r) {
+                close(fds[r][0]);
+                if (write(fds[r][1], params.ncclId, sizeof(params.ncclId)) != (ssize_t)sizeof(params.ncclId)) return 3;
+                close(fds[r][1]);
+            }
+        }
+        params.device += params.rank;
+    }
 
     printf("-----------------------------------------------------------\n");
     printf("  L         OOO      RRRR       A      DDDD       SSS \n");
@@ -439,6 +490,10 @@ close_log:
 cleanup:
     lh_free_solver(S);
     lh_free_sdpa(&data);
+    for (int k = 0; k < nkids; ++k) { /* rank 0 reaps the other ranks; a failed rank fails the run */
+        int st = 0;
+        if (waitpid(kids[k], &st, 0) > 0 && (!WIFEXITED(st) || WEXITSTATUS(st) != 0) && exit_code == 0) exit_code = 3;
+    }
     return exit_code;
 }
 

@@ -43,6 +43,7 @@ int lh_setup_problem(lh_solver *S, const lh_sdpa *d, const lh_params *p)
         fprintf(stderr, "lorads_b200: %s\n", lgpu_last_error(NULL));
         return LH_RET_DEVICE;
     }
+    if (p->ranks > 1) GPU_TRY(S, lgpu_comm_init(S->gpu, p->ncclId, p->rank, p->ranks));
     GPU_TRY(S, lgpu_set_problem(S->gpu, d->m, d->b, (int)d->nBlks, d->blkDims, d->nLpCols));
     if (d->nLpCols > 0) GPU_TRY(S, lgpu_lp_upload(S->gpu, d->lpBeg, d->lpIdx, d->lpElem));
     for (int64_t c = 0; c < d->nBlks; ++c) {

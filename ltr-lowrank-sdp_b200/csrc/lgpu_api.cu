@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <type_traits>
 #include <unordered_map>
@@ -583,7 +584,7 @@ extern "C" void lgpu_destroy(lgpu_ctx *ctx)
     dev_free(ctx->mtmp);
     dev_free(ctx->lp.obj); dev_free(ctx->lp.r_ptr); dev_free(ctx->lp.r_col); dev_free(ctx->lp.r_val);
     dev_free(ctx->lp.c_ptr); dev_free(ctx->lp.c_row); dev_free(ctx->lp.c_val); dev_free(ctx->lp.nrm2sq);
-    dev_free(ctx->send_idx);
+    dev_free(ctx->send_idx); dev_free(ctx->halo_gid);
     dev_free(ctx->dsc); dev_free(ctx->partials); dev_free(ctx->counter);
     prof_flush(ctx);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((lg_ncclComm_t)ctx->comm);
@@ -1037,6 +1038,12 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
             for (auto &cj : lf_col) cj = remap[cj];
             dev_free(ctx->send_idx);
             TRY(dev_upload(ctx, &ctx->send_idx, send_idx));
+            /* halo row k holds global row halo_gid[k] (owners in rank order, ascending inside an owner) */
+            std::vector<int32_t> hg((size_t)ctx->halo_rows);
+            for (int64_t jg = 0; jg < n; ++jg)
+                if ((jg < lo || jg >= hi) && remap[jg] >= 0) hg[remap[jg] - rpr] = (int32_t)jg;
+            dev_free(ctx->halo_gid);
+            TRY(dev_upload(ctx, &ctx->halo_gid, hg));
         }
         std::vector<double> lmc_val((size_t)(e1 - e0)), lrc_a(rc_a.begin() + k0, rc_a.begin() + k1);
         for (int64_t i = 0; i <= nl; ++i) { lf_ptr[i] = f_ptr[lo + i] - e0; lrc_ptr[i] = rc_ptr[lo + i] - k0; }
@@ -1232,8 +1239,8 @@ extern "C" int lgpu_obj_scale(lgpu_ctx *ctx, double s)
     CU(ctx, cudaSetDevice(ctx->device));
     for (auto &c : ctx->cones) {
         double *cv = c.cval, *cc = c.c_coef;
-        launch_map(ctx, c.nnzP, [=] __device__(int64_t i) { cv[i] *= s; });
-        launch_map(ctx, c.nnzC, [=] __device__(int64_t i) { cc[i] *= s; });
+        if (cv) launch_map(ctx, c.nnzP, [=] __device__(int64_t i) { cv[i] *= s; }); /* (a partitioned rank keeps only mc_val) */
+        if (cc) launch_map(ctx, c.nnzC, [=] __device__(int64_t i) { cc[i] *= s; });
         if (c.mc_val) {
             double *mv = c.mc_val;
             launch_map(ctx, c.nnzF, [=] __device__(int64_t i) { mv[i] *= s; });
@@ -1551,7 +1558,7 @@ extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
             DevCone &cn = ctx->cones[c];
             Prof pr(ctx, KC_LAYOUT);
             k_restride_aug<<<grid_for(ctx, cn.n * cn.ld), LGPU_TPB, 0, ctx->stream>>>(
-                cn.n, (int)o_r[c], (int)o_ld[c], (int)cn.r, (int)cn.ld, olds[w] + o_off[c], news[w] + cn.off, 1);
+                cn.n, (int)o_r[c], (int)o_ld[c], (int)cn.r, (int)cn.ld, olds[w] + o_off[c], news[w] + cn.off, 1, cn.n_glob, cn.row_lo);
         }
         if (ctx->lp.n > 0)
             CU(ctx, cudaMemcpyAsync(news[w] + ctx->lp.off, olds[w] + o_lp_off, sizeof(double) * ctx->lp.n,
@@ -2587,20 +2594,140 @@ __global__ void __launch_bounds__(LGPU_TPB) k_basis_update(int64_t n, int k, con
     }
 }
 
+/* S q for the partitioned fused layout: this rank's rows of (C - Diag(sum_k lambda_k a_k)) q into w at their GLOBAL
+ * positions; q is a replicated full-length vector.  Column ids are global (all-gather mode) or local/halo ids that
+ * halo_gid maps back to global rows. */
+__global__ void __launch_bounds__(LGPU_TPB) k_lanczos_symv_part(int64_t nloc, int64_t row_lo, int64_t nsplit,
+                                                                const int32_t *__restrict__ fp, const int32_t *__restrict__ fc,
+                                                                const double *__restrict__ fv, const int32_t *__restrict__ halo_gid,
+                                                                const int32_t *__restrict__ rcptr, const int32_t *__restrict__ rcgid,
+                                                                const double *__restrict__ rca, const double *__restrict__ lam,
+                                                                const double *__restrict__ q, double *__restrict__ w)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < nloc; i += warps) {
+        double a = 0.0;
+        for (int e = fp[i] + lane; e < fp[i + 1]; e += 32) {
+            const int col = fc[e];
+            const int64_t g = halo_gid ? (col < nsplit ? row_lo + col : (int64_t)halo_gid[col - nsplit]) : (int64_t)col;
+            a = fma(fv[e], q[g], a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) {
+            double d = 0.0;
+            for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) d = fma(lam[rcgid[t]], rca[t], d);
+            w[row_lo + i] = fma(-d, q[row_lo + i], a);
+        }
+    }
+}
+
+/* Lanczos for the smallest eigenvalue of a symmetric operator of dimension n.  `apply(qk, qm, bprev, w)` must leave
+ * w = S qk - bprev qm (qm may be null) and dsc[SC_LANCZOS] = <qk, S qk>.  Stop: Ritz residual |beta_k s_k| <= 1e-6 x
+ * (spectral scale of T_k).  Small problems keep the whole Krylov basis and re-orthogonalise against it (two launches per
+ * step); large ones run the plain three-term recurrence, whose extreme Ritz value stays accurate without it. */
+typedef std::function<int(const double *, const double *, double, double *)> LanczosApply;
+static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const LanczosApply &apply, double *theta_out)
+{
+    double *dsc = ctx->dsc;
+    const int kmax = (int)std::min<int64_t>(n, 300);
+    const bool full = (double)vec_len * (double)(kmax + 1) * 8.0 <= 256.0e6;
+    const size_t vec = (size_t)vec_len;
+    const size_t nvec = full ? (size_t)kmax + 2 : 4;
+    TRY(ensure_dstage(ctx, sizeof(double) * (vec * nvec + (size_t)kmax + 8)));
+    double *Q = (double *)ctx->dstage; /* full: q_0 .. q_kmax ; else ring of 3 */
+    double *w = Q + vec * (nvec - 1);
+    double *hbuf = w + vec;
+    CU(ctx, cudaMemsetAsync(Q, 0, sizeof(double) * vec * nvec, ctx->stream)); /* padding entries stay zero */
+    auto qptr = [&](int k) { return Q + vec * (size_t)(full ? k : (k % 3)); };
+    {
+        double *q0 = qptr(0);
+        launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
+            uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+            z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+            const double v = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+            q0[i] = v;
+            acc[0] = fma(v, v, acc[0]);
+        }, slot1(SC_LANCZOS));
+        launch_map(ctx, n, [=] __device__(int64_t i) { q0[i] /= sqrt(dsc[SC_LANCZOS]); });
+    }
+    std::vector<double> al, be;
+    double theta = 0.0;
+    for (int k = 0; k < kmax; ++k) {
+        const double *qk = qptr(k);
+        const double *qm = k > 0 ? qptr(k - 1) : nullptr;
+        const double bprev = k > 0 ? be[k - 1] : 0.0;
+        TRY(apply(qk, qm, bprev, w));
+        /* w -= alpha_k q_k ; then (small problems) against the whole basis ; beta_k = |w| */
+        launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS], qk[i], w[i]); });
+        if (full) {
+            {
+                Prof pr(ctx, KC_REDUCE);
+                k_basis_dots<<<k + 1, LGPU_TPB, 0, ctx->stream>>>(vec_len, Q, w, hbuf);
+            }
+            {
+                Prof pr(ctx, KC_VEC);
+                k_basis_update<<<grid_for(ctx, n, (const void *)k_basis_update), LGPU_TPB, 0, ctx->stream>>>(vec_len, k + 1, Q, hbuf, w);
+            }
+        }
+        launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 1));
+        CHECK_LAUNCH(ctx);
+        TRY(fetch_scalars(ctx, SC_LANCZOS, 2));
+        al.push_back(ctx->hsc[SC_LANCZOS]);
+        const double bnorm = sqrt(ctx->hsc[SC_LANCZOS + 1]);
+        be.push_back(bnorm);
+        theta = tridiag_extreme_eig(al, be, k + 1, -1);
+        const double top = tridiag_extreme_eig(al, be, k + 1, +1);
+        const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
+        const double resid = bnorm * tridiag_last_component(al, be, k + 1, theta);
+        if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale || k + 1 >= kmax) break;
+        double *qn = qptr(k + 1);
+        const double inv = 1.0 / bnorm;
+        launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * inv; });
+    }
+    *theta_out = theta;
+    return 0;
+}
+
 /* calculate_dual_infeasibility_solver (lorads_solver.c:1396-1426, lorads_sdp_conic.c:1636-1699): the reference asks
  * ARPACK (dsaupd/dseupd, "SA", nev = 1, tol = 1e-2) for lambda_min(C - A^*(lambda)) of every cone.  Here: Lanczos on the
- * device, S applied through the full symmetric CSR (sdp_coeff.mv, lorads_sdp_data.c:772-787,983-1006), stopped on the
- * Ritz residual |beta_k s_k| <= 1e-6 x (spectral scale of T_k).  Small cones keep the whole Krylov basis and
- * re-orthogonalise against it (two launches per step); large ones run the plain three-term recurrence, whose extreme
- * Ritz value stays accurate without it. */
+ * device.  One GPU: S on the pattern, applied through the full symmetric CSR (sdp_coeff.mv, lorads_sdp_data.c:772-787,
+ * 983-1006).  Partitioned (fused layout): the Lanczos vectors are replicated full-length vectors, every rank applies its
+ * rows of S and the pieces are all-gathered; all other vector work is done redundantly on every rank, so every rank
+ * obtains the same scalars without further reductions. */
 extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
 {
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
-    if (ctx->world > 1) LGPU_FAIL(ctx, "dual infeasibility is not partitioned in this build (run it on one GPU)");
     double total = 0.0;
+    if (ctx->world > 1) {
+        DevCone &c = ctx->cones[0];
+        const int64_t n = c.n_glob, vec_len = (int64_t)ctx->world * c.n_alloc;
+        const int32_t *hg = ctx->use_halo ? ctx->halo_gid : nullptr;
+        double theta = 0.0;
+        ctx->defer_allreduce = true; /* full-length replicated vectors: the reductions below are already global */
+        auto apply = [&](const double *qk, const double *qm, double bprev, double *w) -> int {
+            {
+                Prof pr(ctx, KC_SPMM);
+                k_lanczos_symv_part<<<grid_for(ctx, c.n * 32, (const void *)k_lanczos_symv_part), LGPU_TPB, 0, ctx->stream>>>(
+                    c.n, c.row_lo, c.n_alloc, c.f_ptr, c.f_col, c.mc_val, hg, c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, qk, w);
+            }
+            NC(ctx, g_nccl.AllGather(w + (size_t)ctx->rank * c.n_alloc, w, (size_t)c.n_alloc, LG_NCCL_FLOAT64,
+                                     (lg_ncclComm_t)ctx->comm, ctx->stream));
+            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double a = w[i];
+                acc[0] = fma(qk[i], a, acc[0]);
+                if (qm) w[i] = fma(-bprev, qm[i], a);
+            }, slot1(SC_LANCZOS));
+            return 0;
+        };
+        const int rc = lanczos_min_eig(ctx, n, vec_len, apply, &theta);
+        ctx->defer_allreduce = false;
+        if (rc) return rc;
+        *sum_neg_eig = fabs(std::min(theta, 0.0));
+        return 0;
+    }
     /* LP part (lorads_solver.c:1404-1412): |min(c_j - a_j^T lambda, 0)| */
-    double *dsc = ctx->dsc;
     if (ctx->lp.n > 0) {
         const int32_t *cp = ctx->lp.c_ptr, *cr = ctx->lp.c_row;
         const double *cv = ctx->lp.c_val, *obj = ctx->lp.obj, *lam = ctx->lam;
@@ -2614,70 +2741,19 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
         total += ctx->hsc[SC_LANCZOS + 2];
     }
     for (auto &c : ctx->cones) {
-        const int64_t n = c.n;
-        const int kmax = (int)std::min<int64_t>(n, 300);
-        const bool full = (double)n * (double)(kmax + 1) * 8.0 <= 256.0e6; /* keep the basis only while it is small */
         /* slack S = C - sum lambda_i A_i on the pattern */
         run_wsum(ctx, c, ctx->lam, true, true, -1.0, c.S);
-        const size_t vec = (size_t)n;
-        const size_t nvec = full ? (size_t)kmax + 2 : 4;
-        TRY(ensure_dstage(ctx, sizeof(double) * (vec * nvec + (size_t)kmax + 8)));
-        double *Q = (double *)ctx->dstage;       /* full: q_0 .. q_kmax ; else ring of 3 */
-        double *w = Q + vec * (nvec - 1);
-        double *hbuf = w + vec;
-        auto qptr = [&](int k) { return Q + vec * (size_t)(full ? k : (k % 3)); };
-        {
-            double *q0 = qptr(0);
-            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
-                uint64_t z = 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
-                z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
-                const double v = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
-                q0[i] = v;
-                acc[0] = fma(v, v, acc[0]);
-            }, slot1(SC_LANCZOS));
-            launch_map(ctx, n, [=] __device__(int64_t i) { q0[i] /= sqrt(dsc[SC_LANCZOS]); });
-        }
-        std::vector<double> al, be;
-        double theta = 0.0;
         const int32_t *fp = c.f_ptr, *fc = c.f_col, *fs = c.f_slot;
         const double *Sv = c.S;
-        for (int k = 0; k < kmax; ++k) {
-            const double *qk = qptr(k);
-            const double *qm = k > 0 ? qptr(k - 1) : nullptr;
-            const double bprev = k > 0 ? be[k - 1] : 0.0;
-            /* w = S q_k - beta_{k-1} q_{k-1} and alpha_k = <q_k, S q_k> */
-            {
-                Prof pr(ctx, KC_SPMM);
-                k_lanczos_symv<<<grid_for(ctx, n * 32, (const void *)k_lanczos_symv), LGPU_TPB, 0, ctx->stream>>>(
-                    n, fp, fc, fs, Sv, qk, qm, bprev, w, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_LANCZOS));
-            }
-            /* w -= alpha_k q_k ; then (small cones) against the whole basis ; beta_k = |w| */
-            launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS], qk[i], w[i]); });
-            if (full) {
-                {
-                    Prof pr(ctx, KC_REDUCE);
-                    k_basis_dots<<<k + 1, LGPU_TPB, 0, ctx->stream>>>(n, Q, w, hbuf);
-                }
-                {
-                    Prof pr(ctx, KC_VEC);
-                    k_basis_update<<<grid_for(ctx, n, (const void *)k_basis_update), LGPU_TPB, 0, ctx->stream>>>(n, k + 1, Q, hbuf, w);
-                }
-            }
-            launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 1));
-            CHECK_LAUNCH(ctx);
-            TRY(fetch_scalars(ctx, SC_LANCZOS, 2));
-            al.push_back(ctx->hsc[SC_LANCZOS]);
-            const double bnorm = sqrt(ctx->hsc[SC_LANCZOS + 1]);
-            be.push_back(bnorm);
-            theta = tridiag_extreme_eig(al, be, k + 1, -1);
-            const double top = tridiag_extreme_eig(al, be, k + 1, +1);
-            const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
-            const double resid = bnorm * tridiag_last_component(al, be, k + 1, theta);
-            if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale || k + 1 >= kmax) break;
-            double *qn = qptr(k + 1);
-            const double inv = 1.0 / bnorm;
-            launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * inv; });
-        }
+        const int64_t n = c.n;
+        double theta = 0.0;
+        auto apply = [&](const double *qk, const double *qm, double bprev, double *w) -> int {
+            Prof pr(ctx, KC_SPMM);
+            k_lanczos_symv<<<grid_for(ctx, n * 32, (const void *)k_lanczos_symv), LGPU_TPB, 0, ctx->stream>>>(
+                n, fp, fc, fs, Sv, qk, qm, bprev, w, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_LANCZOS));
+            return 0;
+        };
+        TRY(lanczos_min_eig(ctx, n, n, apply, &theta));
         total += fabs(std::min(theta, 0.0));
     }
     *sum_neg_eig = total;

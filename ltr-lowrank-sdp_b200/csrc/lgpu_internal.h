@@ -183,6 +183,7 @@ struct lgpu_ctx {
     int64_t halo_rows = 0, send_rows = 0;
     std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt; /* per peer, in rows */
     int32_t *send_idx = nullptr; /* [send_rows] local row to pack, grouped by destination */
+    int32_t *halo_gid = nullptr; /* [halo_rows] global row of each halo row */
     double *sendbuf = nullptr;   /* [send_rows * ld] */
     double *halo = nullptr;      /* [halo_rows * ld] */
     /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */

@@ -520,18 +520,19 @@ __global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, 
  * new column r_old + j gets 1/sqrt(dr) at row j (j < min(n, dr))      lorads_solver.c:1096-1106,1180-1214 */
 __global__ void __launch_bounds__(LGPU_TPB) k_restride_aug(int64_t n, int r_old, int ld_old, int r_new, int ld_new,
                                                            const double *__restrict__ src, double *__restrict__ dst,
-                                                           int plant)
+                                                           int plant, int64_t n_glob, int64_t row_lo)
 {
+    /* n rows of this rank, global rows row_lo .. row_lo + n of a cone of dimension n_glob */
     const int64_t total = n * (int64_t)ld_new;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int dr = r_new - r_old;
-    const double seed = dr > 0 ? 1.0 / sqrt((double)(n < dr ? n : dr)) : 0.0;
+    const double seed = dr > 0 ? 1.0 / sqrt((double)(n_glob < dr ? n_glob : dr)) : 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int64_t row = i / ld_new;
         const int col = (int)(i - row * ld_new);
         double v = 0.0;
         if (col < r_old) v = src[(size_t)row * ld_old + col];
-        else if (plant && col < r_new && (int64_t)(col - r_old) == row) v = seed;
+        else if (plant && col < r_new && (int64_t)(col - r_old) == row + row_lo) v = seed;
         dst[i] = v;
     }
 }

@@ -27,3 +27,46 @@ def test_partitioned_run_matches_single_gpu(built, world, graph, halo):
            "127.0.0.1", "--master-port", str(29740 + world), os.path.join(ROOT, "tests", "_multi_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("graph", ["torus", "random"])
+def test_binary_partitioned_run(built, tmp_path, graph):
+    """the drop-in binary with --ranks 2 (forks one process per GPU, NCCL id over pipes) against the same binary on one
+    GPU: same iteration counts, objective to 1e-6, same status; includes the partitioned dual infeasibility"""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    lb = built
+    if graph == "torus":
+        n = 101 * 199
+        ei, ej, w = lb.torus_graph(101, 199, 81)
+    else:
+        n = 20001
+        ei, ej, w = lb.random_graph(n, 5, 3)
+        import numpy as np
+        w = np.random.default_rng(3).choice([-1.0, 1.0], size=len(ei))
+    inst = tmp_path / "g.dat-s"
+    lb.write_sdpa(str(inst), lb.maxcut_problem(n, ei, ej, w))
+    flags = ["--phase1Tol", "1e-2", "--heuristicFactor", "10", "--reoptLevel", "0", "--timeSecLimit", "600"]
+    res = {}
+    for ranks in (1, 2):
+        jf = tmp_path / f"r{ranks}.json"
+        out = lb.run_solver([str(inst)] + flags + ["--jsonfile", str(jf)] + (["--ranks", "2"] if ranks == 2 else []), timeout=900)
+        assert out.returncode == 0, out.stderr[-2000:]
+        inner = obj = status = dinf = None
+        for line in out.stdout.splitlines():
+            if line.startswith("ALM OuterIter:"):
+                inner = int(line.split("InnerIter:")[1].split()[0])
+            elif "1.Primal Objective:" in line:
+                obj = float(line.split(":")[-1])
+            elif "2.Dual Infeasibility(1)" in line:
+                dinf = float(line.split(":")[-1])
+            elif line.startswith("End Program"):
+                status = line.strip()
+        res[ranks] = (inner, obj, status, dinf, json.load(open(jf))["metrics"])
+    a, b = res[2], res[1]
+    assert a[2] == b[2]
+    assert abs(a[0] - b[0]) <= max(3, 0.05 * b[0]), (a[0], b[0])
+    assert abs(a[1] - b[1]) <= 1e-6 * abs(b[1]), (a[1], b[1])
+    assert abs(a[3] - b[3]) <= 1e-6 + 0.05 * abs(b[3]), (a[3], b[3])
