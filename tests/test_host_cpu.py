@@ -181,3 +181,36 @@ def test_synthetic_builders(built):
     assert info["nnzP"] == len(ei) + 5000
     ti, tj, tw = lb.torus_graph(100, 200, 81)
     assert len(ti) == 40000 and set(np.unique(tw)) == {-1.0, 1.0}              # G81-like: 2 edges per vertex
+
+
+def test_cli_surface_matches_reference_options(built, tmp_path):
+    """argv contract (main.c:125-154, 264-350): positional instance first, the 27 long options parsed with atof/atoi and
+    echoed, rhoCellingADMM always reset to 200 x rhoMax, unknown options ignored, plus the three options benchmark.py
+    passes.  Runs on CPU: the echo happens before the device is touched (the run then stops for lack of a GPU)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: covered by the end-to-end tests")
+    except Exception:
+        pass
+    sched = tmp_path / "r_sched.json"
+    sched.write_text('{"rank_schedule": [5, 8, 12], "schedule_length": 3}')
+    r = built.run_solver([inst_path("G11"), "--phase1Tol", "1e-2", "--heuristicFactor", "10", "--rhoMax", "4000", "--rhoCellingADMM", "7",
+                          "--timeSecLimit", "77", "--reoptLevel", "0", "--fixedRank", "9", "--initRank", "6", "--maxALMIter", "12",
+                          "--lbfgsListLength", "3", "--oracleRankNaive", "--rankSchedule", str(sched), "--nearStallFactor", "0.7",
+                          "--disableOracle", "--noSuchOption", "--jsonfile", str(tmp_path / "o.json")])
+    out = r.stdout
+    for needle in ("phase1Tol = 0.010000", "heuristicFactor = 10.000000", "rhoMax = 4000.000000", "rhoCellingADMM = 800000.000000",
+                   "timeSecLimit = 77.000000", "reoptLevel = 0", "fixedRank = 9", "initRank = 6", "maxALMIter = 12",
+                   "lbfgsListLength = 3", "oracleRankMethod = 1", "disableOracle = 1", "nearStallFactor = 0.700000",
+                   "nConstrs = 800, sdp nBlks = 1, lp Cols = 0", "Pre-solver starts"):
+        assert needle in out, needle
+    assert "unrecognized option" in r.stderr          # glibc getopt reports it and the run goes on, like the reference
+    assert r.returncode == 3 and not (tmp_path / "o.json").exists()
+
+
+def test_partition_and_classify_need_no_gpu(built):
+    assert built.partition_rows(10_000_000, 8, 7) == (8_750_000, 10_000_000, 1_250_000)
+    p = built.read_sdpa(inst_path("multiblock_lp"))
+    infos = [built.cone_classify(p, c) for c in range(p.ncones)]
+    assert all(not i["diag_only"] for i in infos) and len(infos) == 4
