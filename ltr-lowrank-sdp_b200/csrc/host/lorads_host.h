@@ -119,6 +119,11 @@ typedef struct {
 } lh_solver;
 
 double lh_time(void);
+
+/* glibc_rand.c: glibc's srand()/rand() value stream, lock-free */
+void lh_srand(unsigned int seed);
+int lh_rand(void);
+void lh_random_fill(double *a, int64_t n);
 void lh_log(lh_solver *S, const char *fmt, ...);
 
 /* setup */

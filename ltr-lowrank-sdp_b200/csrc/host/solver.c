@@ -97,15 +97,6 @@ void lh_determine_rank(lh_solver *S, const lh_params *p)
     }
 }
 
-/* element k of a factor, in column-major memory order: rand()/RAND_MAX - rand()/RAND_MAX */
-static void random_fill(double *a, int64_t n)
-{
-    for (int64_t i = 0; i < n; ++i) {
-        a[i] = (double)rand() / RAND_MAX;
-        a[i] -= (double)rand() / RAND_MAX;
-    }
-}
-
 int lh_init_variables(lh_solver *S, const lh_params *p)
 {
     GPU_TRY(S, lgpu_alloc_vars(S->gpu, S->rank, (int)p->lbfgsListLength));
@@ -116,23 +107,23 @@ int lh_init_variables(lh_solver *S, const lh_params *p)
     if (!buf) return LH_RET_DEVICE;
     /* the reference draws from ONE glibc rand() stream in this order: R of every cone, rLp, then uLp, vLp,
      * then per cone U, V (lorads_solver.c:625-669, 864-906) */
-    srand(925);
+    lh_srand(925); /* glibc_rand.c: the C library's stream without its per-call lock */
     for (int64_t c = 0; c < S->nCones; ++c) {
-        random_fill(buf, S->blkDims[c] * S->rank[c]);
+        lh_random_fill(buf, S->blkDims[c] * S->rank[c]);
         GPU_TRY(S, lgpu_set_factor(S->gpu, LGPU_R, (int)c, buf));
     }
     if (S->nLpCols > 0) {
-        random_fill(buf, S->nLpCols);
+        lh_random_fill(buf, S->nLpCols);
         GPU_TRY(S, lgpu_set_lp(S->gpu, LGPU_R, buf));
-        random_fill(buf, S->nLpCols);
+        lh_random_fill(buf, S->nLpCols);
         GPU_TRY(S, lgpu_set_lp(S->gpu, LGPU_U, buf));
-        random_fill(buf, S->nLpCols);
+        lh_random_fill(buf, S->nLpCols);
         GPU_TRY(S, lgpu_set_lp(S->gpu, LGPU_V, buf));
     }
     for (int64_t c = 0; c < S->nCones; ++c) {
-        random_fill(buf, S->blkDims[c] * S->rank[c]);
+        lh_random_fill(buf, S->blkDims[c] * S->rank[c]);
         GPU_TRY(S, lgpu_set_factor(S->gpu, LGPU_U, (int)c, buf));
-        random_fill(buf, S->blkDims[c] * S->rank[c]);
+        lh_random_fill(buf, S->blkDims[c] * S->rank[c]);
         GPU_TRY(S, lgpu_set_factor(S->gpu, LGPU_V, (int)c, buf));
     }
     free(buf);

@@ -214,3 +214,108 @@ def test_partition_and_classify_need_no_gpu(built):
     p = built.read_sdpa(inst_path("multiblock_lp"))
     infos = [built.cone_classify(p, c) for c in range(p.ncones)]
     assert all(not i["diag_only"] for i in infos) and len(infos) == 4
+
+
+def test_rand_stream_is_glibc_rand(built):
+    """The starting point must be the reference's srand(925) stream (lorads_solver.c:529-539): the lock-free
+    restatement in csrc/host/glibc_rand.c against the C library, number for number, and the factor fill."""
+    H = built.host_lib()
+    libc = ctypes.CDLL("libc.so.6")
+    H.lh_random_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+    for seed in (925, 0, 1, 20000, 2 ** 31 + 5):
+        libc.srand(ctypes.c_uint(seed))
+        H.lh_srand(ctypes.c_uint(seed))
+        assert [libc.rand() for _ in range(5000)] == [H.lh_rand() for _ in range(5000)], seed
+    libc.srand(925)
+    H.lh_srand(925)
+    n = 20011
+    got = np.empty(n)
+    H.lh_random_fill(got.ctypes.data, n)
+    want = np.empty(n)
+    for i in range(n):
+        x = libc.rand() / 2147483647
+        x -= libc.rand() / 2147483647
+        want[i] = x
+    assert np.array_equal(got, want)
+    assert libc.rand() == H.lh_rand()  # the fill leaves the stream where the library's would be
+
+
+def _random_sdpa_text(rng, m, dims, nlp, count, long_objective=0):
+    """Entry lines in random order, both triangles, duplicates, assorted number spellings."""
+    spell = [lambda v: repr(v), lambda v: "%.17g" % v, lambda v: "%.3e" % v, lambda v: "%+.6f" % v, lambda v: "%.12E" % v,
+             lambda v: ("%.4f" % v).replace("0.", ".", 1), lambda v: "%d." % round(v * 10), lambda v: "%d" % round(v * 10)]
+    lines, want = [], []
+    nblk = len(dims) + (1 if nlp else 0)
+    for k in range(count):
+        con = int(rng.integers(0, m + 1))
+        if k < long_objective:
+            con = 0
+        blk = int(rng.integers(0, nblk)) if k >= long_objective else 0
+        v = float(rng.normal()) * 10 ** int(rng.integers(-3, 4))
+        txt = spell[int(rng.integers(0, len(spell)))](v)
+        if abs(float(txt)) < 1e-12:
+            txt = "1.5"
+        if blk < len(dims):
+            n = dims[blk]
+            i, j = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+        else:
+            i = j = int(rng.integers(1, nlp + 1))
+        sep = ["  ", " ", "\t"][int(rng.integers(0, 3))]
+        lines.append(sep.join(str(x) for x in (con, blk + 1, i, j)) + sep + txt + ("\r" if k % 11 == 0 else ""))
+        want.append((con, blk, i - 1, j - 1, -float(txt) if con == 0 else float(txt)))
+    head = '"generated\n%d\n%d\n%s\n%s\n' % (m, nblk, " ".join(str(d) for d in list(dims) + ([-nlp] if nlp else [])),
+                                              " ".join(repr(float(x)) for x in rng.normal(size=m)))
+    return head + "\n".join(lines) + "\n", want
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5, 8])
+def test_reader_threads_and_number_formats(built, tmp_path, monkeypatch, threads):
+    """the multi-threaded reader gives the single-threaded answer -- column order = file order then
+    ascending packed index, every value bit-identical to float(text) -- for any thread count, including columns long
+    enough for the cooperative sort."""
+    rng = np.random.default_rng(100 + threads)
+    m, dims, nlp = 7, [400, 3], 5
+    text, want = _random_sdpa_text(rng, m, dims, nlp, count=90000, long_objective=70000)
+    f = tmp_path / "rnd.dat-s"
+    f.write_text(text)
+    monkeypatch.setenv("LORADS_READ_THREADS", str(threads))
+    p = built.read_sdpa(str(f))
+    assert p.m == m and list(p.dims) == dims and p.nlp == nlp
+    # expectation, built straight from the generated lines
+    cols = [[[] for _ in range(m + 1)] for _ in range(len(dims) + 1)]
+    for con, blk, i, j, v in want:
+        if blk < len(dims):
+            n = dims[blk]
+            lo, hi = min(i, j), max(i, j)
+            cols[blk][con].append(((2 * n - lo - 1) * lo // 2 + hi, v))
+        else:
+            cols[blk][con].append((i, v))
+    for k in range(len(dims)):
+        beg = p.mat_beg[k]
+        assert beg[-1] == sum(len(c) for c in cols[k])
+        for c in range(m + 1):
+            exp = sorted(cols[k][c], key=lambda t: t[0])  # python's sort is stable: ties stay in file order
+            assert p.mat_idx[k][beg[c]:beg[c + 1]].tolist() == [t[0] for t in exp], (k, c)
+            got = p.mat_elem[k][beg[c]:beg[c + 1]]
+            assert got.tobytes() == np.array([t[1] for t in exp], dtype=np.float64).tobytes(), (k, c)
+    for c in range(m + 1):
+        exp = cols[len(dims)][c]  # LP: file order inside the column
+        assert p.lp_idx[p.lp_beg[c]:p.lp_beg[c + 1]].tolist() == [t[0] for t in exp]
+        assert p.lp_elem[p.lp_beg[c]:p.lp_beg[c + 1]].tobytes() == np.array([t[1] for t in exp]).tobytes()
+
+
+def test_reader_number_conversion_is_strtod(built, tmp_path, monkeypatch):
+    """the fast decimal path and the library path agree with float() on awkward spellings"""
+    toks = ["1", "-1", "+1", "0.5", ".5", "5.", "1e0", "1E+3", "1e-3", "123456789012345678", "1234567890123456789012",
+            "0.1", "0.30000000000000004", "9007199254740993", "9007199254740992", "1e22", "1e23", "1e-22", "1e-23",
+            "4.9e-324", "1.7976931348623157e308", "2.2250738585072014e-308", "0.000000000000000000000001234",
+            "123456.789e-5", "00012.5000", "-0.25e+1", "7.", "3.14159265358979323846264338327950288"]
+    f = tmp_path / "num.dat-s"
+    n = len(toks)
+    f.write_text("1\n1\n%d\n1.0\n" % n + "".join("1 1 %d %d %s\n" % (k + 1, k + 1, t) for k, t in enumerate(toks)))
+    for thr in ("1", "3"):
+        monkeypatch.setenv("LORADS_READ_THREADS", thr)
+        p = built.read_sdpa(str(f))
+        beg = p.mat_beg[0]
+        keep = [float(t) for t in toks if abs(float(t)) >= 1e-12]
+        assert p.mat_elem[0][beg[1]:beg[2]].tobytes() == np.array(keep).tobytes()
