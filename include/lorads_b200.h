@@ -79,6 +79,21 @@ int lgpu_lp_upload(lgpu_ctx *ctx, const int64_t *lp_beg, const int64_t *lp_idx, 
 int lgpu_cone_info(const lgpu_ctx *ctx, int cone, int64_t out[6]);
 /* the same six facts from the reader's arrays alone: pure host code, needs neither a context nor a GPU */
 int lgpu_cone_classify(int64_t n, int64_t m, const int64_t *mat_beg, const int64_t *mat_idx, int64_t out[6]);
+/* The device layout of one cone as lgpu_cone_upload would build it for rank `rank` of `world` (world = 1: the
+ * single-GPU layout), again pure host code: build once, read arrays by name, free.  `name` is the array
+ * (csrc/lgpu_layout.h: pat_row, pat_col, cval, c_slot, c_coef, a_ptr, a_slot, a_coef, con_gid, t_ptr, t_loc, t_gid,
+ * t_val, f_ptr, f_col, f_slot, d_row, d_val, mc_val, rc_ptr, rc_gid, rc_a, and for world > 1 lf_ptr, lf_col, lmc_val,
+ * lrc_ptr, lrc_gid, lrc_a, send_idx, halo_gid, send_off, send_cnt, recv_off, recv_cnt) or "scalars" (16 doubles: mA
+ * nnzP nnzA nnzC nnzF max_con_len max_slot_len |C|_1 |C|_2^2 |C|_inf dense sparse_container diag_only use_halo
+ * halo_rows send_rows).  *count receives the number of elements, *elem_bytes 4 (int32), 8 (double) or -8 (int64); at
+ * most cap_bytes are written to out.  An inspection/test entry: the replacement for walking the reference's
+ * sdp_coeff_sparse / lorads_cone_sdp_* structs (def_lorads_sdp_data.h:100-117, def_lorads_sdp_conic.h:131-155). */
+typedef struct lgpu_layout lgpu_layout;
+int lgpu_cone_layout_build(lgpu_layout **out, int64_t n, int64_t m, const int64_t *mat_beg, const int64_t *mat_idx,
+                           const double *mat_elem, int world, int rank);
+int lgpu_cone_layout_get(const lgpu_layout *layout, const char *name, int64_t cap_bytes, void *out, int64_t *count,
+                         int *elem_bytes);
+void lgpu_cone_layout_free(lgpu_layout *layout);
 /* aggregated lower pattern of a cone in the reference's order (sorted by (col,row)) */
 int lgpu_cone_pattern(const lgpu_ctx *ctx, int cone, int64_t cap, int32_t *row, int32_t *col);
 /* cal_sdp_const (lorads_solver.c:1457-1485): out = {|C|_1, |C|_2, |C|_inf, |b|_1, |b|_2, |b|_inf(Q2 quirk)} */

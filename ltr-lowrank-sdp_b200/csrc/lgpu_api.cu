@@ -18,6 +18,7 @@
 
 #include "../../include/lorads_b200.h"
 #include "lgpu_kernels.cuh"
+#include "lgpu_layout.h"
 
 /* ------------------------------------------------------------------------------------------------
  * error handling
@@ -654,74 +655,6 @@ extern "C" int lgpu_set_problem(lgpu_ctx *ctx, int64_t m, const double *b, int n
     return 0;
 }
 
-static inline void unpack_lower(int64_t n, int64_t idx, int64_t *row, int64_t *col)
-{
-    /* column-major packed lower triangle: start(j) = j (2n - j + 1) / 2  (PACK_IDX, lorads_utils.h:167) */
-    double t = (2.0 * (double)n + 1.0);
-    int64_t j = (int64_t)floor((t - sqrt(t * t - 8.0 * (double)idx)) / 2.0);
-    if (j < 0) j = 0;
-    if (j > n - 1) j = n - 1;
-    while (j > 0 && j * (2 * n - j + 1) / 2 > idx) --j;
-    while (j + 1 < n && (j + 1) * (2 * n - j) / 2 <= idx) ++j;
-    *col = j;
-    *row = idx - j * (2 * n - j + 1) / 2 + j;
-}
-
-/* ------------------------------------------------------------------------------------------------
- * The reference's storage rules for one cone (pure host code, no device needed):
- *   coefficient class  ZERO / SPARSE / DENSE by nnz > 10 % of n(n+1)/2        sdpDataMatSetData, lorads_sdp_data.c:1180-1197
- *   container          SPARSE_CONE iff #non-zero A_i <= 0.3 m                  LUserDataChooseCone, lorads_user_data.c:105-109
- *   aggregate          dense iff n < 20, or a dense member, or |union pattern| >= 10 % of the triangle
- *                                                                              AConePresolveData, lorads_sdp_conic.c:1185-1393
- * plus what this library derives: the union pattern (sorted packed indices; empty when dense), nnzA and whether every
- * non-zero constraint is one diagonal entry (MaxCut-type, fused path).
- * ------------------------------------------------------------------------------------------------*/
-struct ConeRules {
-    int obj_type = 0;
-    int64_t mA = 0, nnzA = 0, nnzP = 0;
-    bool sparse_container = false, dense = false, diag_only = false;
-    std::vector<int64_t> pat;
-};
-static void cone_rules(int64_t n, int64_t m, const int64_t *beg, const int64_t *idx, ConeRules &r)
-{
-    const int64_t tri = n * (n + 1) / 2;
-    auto mtype = [&](int64_t nnz) -> int {
-        if (nnz == 0) return 0;
-        if ((double)nnz > 0.1 * (double)tri) return 2;
-        return 1;
-    };
-    r.obj_type = mtype(beg[1] - beg[0]);
-    bool any_dense = r.obj_type == 2;
-    r.mA = 0;
-    bool diag_only = true;
-    for (int64_t col = 1; col <= m; ++col) {
-        const int64_t nnz = beg[col + 1] - beg[col];
-        if (nnz > 0) ++r.mA;
-        if (mtype(nnz) == 2) any_dense = true;
-        if (nnz > 1) diag_only = false;
-        if (nnz == 1 && diag_only) {
-            int64_t rr, cc;
-            unpack_lower(n, idx[beg[col]], &rr, &cc);
-            if (rr != cc) diag_only = false;
-        }
-    }
-    r.diag_only = diag_only && r.mA > 0;
-    r.nnzA = beg[m + 1] - beg[1];
-    r.sparse_container = !((double)r.mA > 0.3 * (double)m);
-    r.dense = (n < 20) || any_dense;
-    r.pat.clear();
-    if (!r.dense) {
-        r.pat.assign(idx, idx + beg[m + 1]);
-        std::sort(r.pat.begin(), r.pat.end());
-        r.pat.erase(std::unique(r.pat.begin(), r.pat.end()), r.pat.end());
-        if ((double)r.pat.size() / (double)tri >= 0.1) {
-            r.dense = true;
-            r.pat.clear();
-        }
-    }
-    r.nnzP = r.dense ? tri : (int64_t)r.pat.size();
-}
-
 /* work list of the CSR rows that k_spmm_long_chunks takes over */
 static int upload_long_rows(lgpu_ctx *ctx, DevCone &c, const std::vector<int32_t> &ptr)
 {
@@ -795,322 +728,157 @@ extern "C" int lgpu_cone_classify(int64_t n, int64_t m, const int64_t *mat_beg, 
     return 0;
 }
 
+struct lgpu_layout {
+    ConeLayout L;
+};
+extern "C" int lgpu_cone_layout_build(lgpu_layout **out, int64_t n, int64_t m, const int64_t *mat_beg, const int64_t *mat_idx,
+                                      const double *mat_elem, int world, int rank)
+{
+    if (!out || n <= 0 || m <= 0 || !mat_beg || world < 1 || rank < 0 || rank >= world) return 1;
+    lgpu_layout *h = new lgpu_layout();
+    std::string err;
+    if (build_cone_layout(n, m, mat_beg, mat_idx, mat_elem, world, rank, true, h->L, err)) { delete h; return 2; }
+    *out = h;
+    return 0;
+}
+extern "C" void lgpu_cone_layout_free(lgpu_layout *layout) { delete layout; }
+extern "C" int lgpu_cone_layout_get(const lgpu_layout *layout, const char *name, int64_t cap_bytes, void *out, int64_t *count,
+                                    int *elem_bytes)
+{
+    if (!layout || !name || !count || !elem_bytes) return 1;
+    const ConeLayout &L = layout->L;
+    *count = 0;
+    *elem_bytes = 0;
+    const std::string nm(name);
+    const void *src = nullptr;
+    bool known = false;
+    std::vector<double> sc;
+#define LQ_ARRAY(field, bytes)                                   \
+    if (nm == #field) {                                          \
+        src = L.field.data();                                    \
+        *count = (int64_t)L.field.size();                        \
+        *elem_bytes = bytes;                                     \
+        known = true;                                            \
+    }
+    LQ_ARRAY(pat_row, 4) LQ_ARRAY(pat_col, 4) LQ_ARRAY(cval, 8) LQ_ARRAY(c_slot, 4) LQ_ARRAY(c_coef, 8) LQ_ARRAY(a_ptr, 4)
+    LQ_ARRAY(a_slot, 4) LQ_ARRAY(a_coef, 8) LQ_ARRAY(con_gid, 4) LQ_ARRAY(t_ptr, 4) LQ_ARRAY(t_loc, 4) LQ_ARRAY(t_gid, 4)
+    LQ_ARRAY(t_val, 8) LQ_ARRAY(f_ptr, 4) LQ_ARRAY(f_col, 4) LQ_ARRAY(f_slot, 4) LQ_ARRAY(d_row, 4) LQ_ARRAY(d_val, 8)
+    LQ_ARRAY(mc_val, 8) LQ_ARRAY(rc_ptr, 4) LQ_ARRAY(rc_gid, 4) LQ_ARRAY(rc_a, 8) LQ_ARRAY(lf_ptr, 4) LQ_ARRAY(lf_col, 4)
+    LQ_ARRAY(lmc_val, 8) LQ_ARRAY(lrc_ptr, 4) LQ_ARRAY(lrc_gid, 4) LQ_ARRAY(lrc_a, 8) LQ_ARRAY(send_idx, 4) LQ_ARRAY(halo_gid, 4)
+    LQ_ARRAY(send_off, -8) LQ_ARRAY(send_cnt, -8) LQ_ARRAY(recv_off, -8) LQ_ARRAY(recv_cnt, -8)
+#undef LQ_ARRAY
+    if (nm == "scalars") {
+        sc = {(double)L.mA, (double)L.nnzP, (double)L.nnzA, (double)L.nnzC, (double)L.nnzF, (double)L.max_con_len,
+              (double)L.max_slot_len, L.c_nrm1, L.c_nrm2sq, L.c_nrminf, L.dense ? 1.0 : 0.0, L.sparse_container ? 1.0 : 0.0,
+              L.diag_only ? 1.0 : 0.0, L.use_halo ? 1.0 : 0.0, (double)L.halo_rows, (double)L.send_rows};
+        src = sc.data();
+        *count = (int64_t)sc.size();
+        *elem_bytes = 8;
+        known = true;
+    }
+    if (!known) return 3;
+    if (out && src && *count > 0) {
+        const int64_t bytes = *count * (int64_t)std::abs(*elem_bytes);
+        memcpy(out, src, (size_t)std::min<int64_t>(bytes, cap_bytes));
+    }
+    return 0;
+}
+
 extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, const int64_t *idx_in, const double *val_in)
 {
     if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     DevCone &c = ctx->cones[cone];
-    const int64_t n = c.n, m = ctx->m;
-    const int64_t tri = n * (n + 1) / 2;
-    const int64_t total = beg[m + 1];
-    /* per-column ascending order (dataMatCreateSparseImpl sorts when needed, lorads_sdp_data.c:100-102) */
-    std::vector<int64_t> idx(idx_in, idx_in + total);
-    std::vector<double> val(val_in, val_in + total);
-    for (int64_t col = 0; col <= m; ++col) {
-        const int64_t e0 = beg[col], e1 = beg[col + 1];
-        bool asc = true;
-        for (int64_t e = e0 + 1; e < e1; ++e)
-            if (idx[e] < idx[e - 1]) { asc = false; break; }
-        if (!asc) {
-            std::vector<int64_t> o(e1 - e0);
-            std::iota(o.begin(), o.end(), (int64_t)0);
-            std::stable_sort(o.begin(), o.end(), [&](int64_t a, int64_t b2) { return idx[e0 + a] < idx[e0 + b2]; });
-            std::vector<int64_t> ti(e1 - e0);
-            std::vector<double> tv(e1 - e0);
-            for (size_t q = 0; q < o.size(); ++q) { ti[q] = idx[e0 + o[q]]; tv[q] = val[e0 + o[q]]; }
-            std::copy(ti.begin(), ti.end(), idx.begin() + e0);
-            std::copy(tv.begin(), tv.end(), val.begin() + e0);
-        }
-    }
-    /* storage rules of the reference, shared with the GPU-less lgpu_cone_classify */
-    ConeRules rules;
-    cone_rules(n, m, beg, idx.data(), rules);
-    c.obj_type = rules.obj_type;
-    const int64_t mA = rules.mA;
-    c.mA = mA;
-    c.sparse_container = rules.sparse_container;
-    bool dense = rules.dense;
-    std::vector<int64_t> pat;
-    pat.swap(rules.pat);
-    c.dense_aggregate = dense;
-    if (dense) {
-        if (tri >= (int64_t)1 << 30) LGPU_FAIL(ctx, "dense aggregate too large for this build (n=%lld)", (long long)n);
-        pat.resize(tri);
-        std::iota(pat.begin(), pat.end(), (int64_t)0);
-    }
-    const int64_t nnzP = (int64_t)pat.size();
-    if (nnzP >= (int64_t)1 << 31 || total >= (int64_t)1 << 31) LGPU_FAIL(ctx, "cone too large for 32-bit device indices");
-    c.nnzP = nnzP;
-    c.h_pat_row.resize(nnzP);
-    c.h_pat_col.resize(nnzP);
-    int64_t ndiag = 0;
-    for (int64_t k = 0; k < nnzP; ++k) {
-        int64_t r, q;
-        unpack_lower(n, pat[k], &r, &q);
-        c.h_pat_row[k] = (int32_t)r;
-        c.h_pat_col[k] = (int32_t)q;
-        if (r == q) ++ndiag;
-    }
-    auto slot_of = [&](int64_t packed) -> int32_t {
-        if (dense) return (int32_t)packed;
-        return (int32_t)(std::lower_bound(pat.begin(), pat.end(), packed) - pat.begin());
-    };
-    /* objective */
-    std::vector<double> cval(nnzP, 0.0), c_coef;
-    std::vector<int32_t> c_slot;
-    c.c_nrm1 = c.c_nrm2sq = c.c_nrminf = 0.0;
-    for (int64_t e = beg[0]; e < beg[1]; ++e) {
-        const int32_t s = slot_of(idx[e]);
-        const bool dg = c.h_pat_row[s] == c.h_pat_col[s];
-        cval[s] += val[e];
-        c_slot.push_back(s);
-        c_coef.push_back(dg ? val[e] : 2.0 * val[e]);
-        c.c_nrm1 += (dg ? 1.0 : 2.0) * fabs(val[e]);
-        c.c_nrm2sq += (dg ? 1.0 : 2.0) * val[e] * val[e];
-        c.c_nrminf = std::max(c.c_nrminf, fabs(val[e]));
-    }
-    c.nnzC = (int64_t)c_slot.size();
-    /* constraints: CSR over non-zero constraints */
-    std::vector<int32_t> a_ptr(1, 0), a_slot, con_gid;
-    std::vector<double> a_coef, a_raw;
-    a_slot.reserve(total);
-    a_coef.reserve(total);
-    a_raw.reserve(total);
-    bool diag_only = mA > 0;
-    std::vector<int32_t> d_row;
-    std::vector<double> d_val;
-    c.max_con_len = 0;
-    for (int64_t col = 1; col <= m; ++col) {
-        const int64_t e0 = beg[col], e1 = beg[col + 1];
-        if (e1 == e0) continue;
-        con_gid.push_back((int32_t)(col - 1));
-        for (int64_t e = e0; e < e1; ++e) {
-            const int32_t s = slot_of(idx[e]);
-            const bool dg = c.h_pat_row[s] == c.h_pat_col[s];
-            a_slot.push_back(s);
-            a_raw.push_back(val[e]);
-            a_coef.push_back(dg ? val[e] : 2.0 * val[e]);
-            if (!dg) diag_only = false;
-        }
-        if (e1 - e0 != 1) diag_only = false;
-        else if (diag_only) { d_row.push_back(c.h_pat_row[a_slot.back()]); d_val.push_back(val[e0]); }
-        c.max_con_len = std::max<int64_t>(c.max_con_len, e1 - e0);
-        a_ptr.push_back((int32_t)a_slot.size());
-    }
-    c.nnzA = (int64_t)a_slot.size();
-    c.diag_only = diag_only;
-    /* transpose by slot: counting sort, stable in constraint order (the reference's accumulation order) */
-    std::vector<int32_t> t_ptr(nnzP + 1, 0), t_loc(c.nnzA), t_gid(c.nnzA);
-    std::vector<double> t_val(c.nnzA);
-    for (int64_t e = 0; e < c.nnzA; ++e) t_ptr[a_slot[e] + 1]++;
-    c.max_slot_len = 0;
-    for (int64_t k = 0; k < nnzP; ++k) {
-        c.max_slot_len = std::max<int64_t>(c.max_slot_len, t_ptr[k + 1]);
-        t_ptr[k + 1] += t_ptr[k];
-    }
+    const int64_t n = c.n_glob > 0 ? c.n_glob : c.n, m = ctx->m;
+    /* all host-side preprocessing (storage rules, pattern, CSR forms, partition slices, exchange plan): lgpu_layout.h */
+    ConeLayout L;
     {
-        std::vector<int32_t> fill(t_ptr.begin(), t_ptr.end() - 1);
-        for (int64_t t = 0; t < mA; ++t)
-            for (int32_t e = a_ptr[t]; e < a_ptr[t + 1]; ++e) {
-                const int32_t p = fill[a_slot[e]]++;
-                t_loc[p] = (int32_t)t;
-                t_gid[p] = con_gid[t];
-                t_val[p] = a_raw[e];
-            }
+        std::string err;
+        if (build_cone_layout(n, m, beg, idx_in, val_in, ctx->world, ctx->rank, ctx->ncones == 1 && ctx->lp.n == 0, L, err))
+            LGPU_FAIL(ctx, "%s", err.c_str());
     }
-    /* full symmetric CSR: row -> (col, slot) */
-    c.nnzF = 2 * nnzP - ndiag;
-    if (c.nnzF >= (int64_t)1 << 31) LGPU_FAIL(ctx, "cone too large for 32-bit device indices");
-    std::vector<int32_t> f_ptr(n + 1, 0), f_col(c.nnzF), f_slot(c.nnzF);
-    for (int64_t k = 0; k < nnzP; ++k) {
-        f_ptr[c.h_pat_row[k] + 1]++;
-        if (c.h_pat_row[k] != c.h_pat_col[k]) f_ptr[c.h_pat_col[k] + 1]++;
-    }
-    for (int64_t i = 0; i < n; ++i) f_ptr[i + 1] += f_ptr[i];
-    {
-        /* pattern is sorted by (col,row): emitting the (col -> row) entries first in k order and the
-         * (row -> col) ones in a second pass keeps every CSR row sorted by column */
-        std::vector<int32_t> fill(f_ptr.begin(), f_ptr.end() - 1);
-        /* entries (i, j) with j < i come from pattern entries with col=j: ascending k visits ascending j */
-        for (int64_t k = 0; k < nnzP; ++k) {
-            const int32_t i = c.h_pat_row[k], j = c.h_pat_col[k];
-            const int32_t p = fill[i]++;
-            f_col[p] = j;
-            f_slot[p] = (int32_t)k;
-        }
-        for (int64_t k = 0; k < nnzP; ++k) {
-            const int32_t i = c.h_pat_row[k], j = c.h_pat_col[k];
-            if (i == j) continue;
-            const int32_t p = fill[j]++;
-            f_col[p] = i;
-            f_slot[p] = (int32_t)k;
-        }
-    }
-    /* upload */
     free_cone(c);
+    c.obj_type = L.obj_type;
+    c.mA = L.mA;
+    c.sparse_container = L.sparse_container;
+    c.dense_aggregate = L.dense;
+    c.diag_only = L.diag_only;
+    c.nnzP = L.nnzP;
+    c.nnzA = L.nnzA;
+    c.nnzC = L.nnzC;
+    c.nnzF = L.nnzF;
+    c.max_con_len = L.max_con_len;
+    c.max_slot_len = L.max_slot_len;
+    c.c_nrm1 = L.c_nrm1;
+    c.c_nrm2sq = L.c_nrm2sq;
+    c.c_nrminf = L.c_nrminf;
+    c.h_pat_row.swap(L.pat_row);
+    c.h_pat_col.swap(L.pat_col);
+    c.n = n;
     c.n_glob = n;
     c.row_lo = 0;
     c.n_alloc = n;
-    c.m_loc = mA;
-    if (ctx->world > 1) {
-        /* row-block partition: this rank keeps the CSR rows, the row -> constraint lists and the vector rows of
-         * [lo, hi); column indices and constraint ids stay global (they index the all-gathered factor and the
-         * replicated-length m-vectors).  Only the fused MaxCut-type layout is partitioned in this build. */
-        if (!(diag_only && mA == m && ctx->ncones == 1 && ctx->lp.n == 0))
-            LGPU_FAIL(ctx, "row-block partitioned runs need one SDP block with single-diagonal-entry constraints (MaxCut-type)");
-        int64_t lo, hi, rpr;
-        lgpu_partition_rows(n, ctx->world, ctx->rank, &lo, &hi, &rpr);
-        const int64_t nl = hi - lo;
-        std::vector<int32_t> rc_ptr(n + 1, 0);
-        for (int64_t t = 0; t < mA; ++t) rc_ptr[d_row[t] + 1]++;
-        for (int64_t i = 0; i < n; ++i) rc_ptr[i + 1] += rc_ptr[i];
-        std::vector<int32_t> rc_gid(mA);
-        std::vector<double> rc_a(mA);
-        {
-            std::vector<int32_t> fill(rc_ptr.begin(), rc_ptr.end() - 1);
-            for (int64_t t = 0; t < mA; ++t) {
-                const int32_t q = fill[d_row[t]]++;
-                rc_gid[q] = con_gid[t];
-                rc_a[q] = d_val[t];
-            }
-        }
-        const int32_t e0 = f_ptr[lo], e1 = f_ptr[hi], k0 = rc_ptr[lo], k1 = rc_ptr[hi];
-        std::vector<int32_t> lf_ptr(nl + 1), lf_col(f_col.begin() + e0, f_col.begin() + e1), lrc_ptr(nl + 1),
-            lrc_gid(rc_gid.begin() + k0, rc_gid.begin() + k1);
-        /* halo plan.  Every rank holds the whole CSR on the host during upload, so it can derive without any
-         * communication both what it needs from each peer and what each peer needs from it (same lists, same
-         * ascending order on both sides). */
-        const int P = ctx->world;
-        ctx->send_off.assign(P, 0); ctx->send_cnt.assign(P, 0); ctx->recv_off.assign(P, 0); ctx->recv_cnt.assign(P, 0);
-        std::vector<int32_t> remap(n, -1), send_idx;
-        {
-            std::vector<uint8_t> mark(n, 0);
-            for (int32_t e = e0; e < e1; ++e) mark[f_col[e]] = 1;
-            int64_t pos = 0;
-            for (int q = 0; q < P; ++q) {
-                int64_t qlo, qhi, qr;
-                lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
-                ctx->recv_off[q] = pos;
-                if (q != ctx->rank)
-                    for (int64_t j = qlo; j < qhi; ++j)
-                        if (mark[j]) remap[j] = (int32_t)(rpr + pos++);
-                ctx->recv_cnt[q] = pos - ctx->recv_off[q];
-            }
-            ctx->halo_rows = pos;
-            for (int64_t j = lo; j < hi; ++j) remap[j] = (int32_t)(j - lo);
-            std::vector<uint8_t> want(nl);
-            for (int q = 0; q < P; ++q) {
-                ctx->send_off[q] = (int64_t)send_idx.size();
-                if (q == ctx->rank) continue;
-                int64_t qlo, qhi, qr;
-                lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
-                std::fill(want.begin(), want.end(), 0);
-                for (int32_t e = f_ptr[qlo]; e < f_ptr[qhi]; ++e) {
-                    const int32_t j = f_col[e];
-                    if (j >= lo && j < hi) want[j - lo] = 1;
-                }
-                for (int64_t j = 0; j < nl; ++j)
-                    if (want[j]) send_idx.push_back((int32_t)j);
-                ctx->send_cnt[q] = (int64_t)send_idx.size() - ctx->send_off[q];
-            }
-            ctx->send_rows = (int64_t)send_idx.size();
-        }
-        /* exchange only what is referenced when that is clearly less than everything (structured graphs: a thin
-         * boundary; uniform random graphs at P = 2: nearly all rows, where the plain all-gather is the better tool) */
-        {
-            /* the choice must be the same on every rank, so it is made from the halo sizes of ALL ranks (each rank
-             * can count them: it holds the whole CSR) */
-            int64_t all_halo = 0;
-            std::vector<uint8_t> seen(n);
-            for (int q = 0; q < P; ++q) {
-                int64_t qlo, qhi, qr;
-                lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
-                std::fill(seen.begin(), seen.end(), 0);
-                for (int32_t e = f_ptr[qlo]; e < f_ptr[qhi]; ++e) {
-                    const int32_t j = f_col[e];
-                    if ((j < qlo || j >= qhi) && !seen[j]) { seen[j] = 1; ++all_halo; }
-                }
-            }
-            ctx->use_halo = (double)all_halo < 0.85 * (double)n * (double)(P - 1);
-        }
-        if (const char *hv = getenv("LORADS_HALO")) ctx->use_halo = atoi(hv) != 0;
-        if (ctx->use_halo) {
-            for (auto &cj : lf_col) cj = remap[cj];
+    c.m_loc = L.mA;
+    if (L.partitioned) {
+        ctx->send_off = L.send_off; ctx->send_cnt = L.send_cnt; ctx->recv_off = L.recv_off; ctx->recv_cnt = L.recv_cnt;
+        ctx->halo_rows = L.halo_rows;
+        ctx->send_rows = L.send_rows;
+        ctx->use_halo = L.use_halo;
+        if (L.use_halo) {
             dev_free(ctx->send_idx);
-            TRY(dev_upload(ctx, &ctx->send_idx, send_idx));
-            /* halo row k holds global row halo_gid[k] (owners in rank order, ascending inside an owner) */
-            std::vector<int32_t> hg((size_t)ctx->halo_rows);
-            for (int64_t jg = 0; jg < n; ++jg)
-                if ((jg < lo || jg >= hi) && remap[jg] >= 0) hg[remap[jg] - rpr] = (int32_t)jg;
+            TRY(dev_upload(ctx, &ctx->send_idx, L.send_idx));
             dev_free(ctx->halo_gid);
-            TRY(dev_upload(ctx, &ctx->halo_gid, hg));
+            TRY(dev_upload(ctx, &ctx->halo_gid, L.halo_gid));
         }
-        std::vector<double> lmc_val((size_t)(e1 - e0)), lrc_a(rc_a.begin() + k0, rc_a.begin() + k1);
-        for (int64_t i = 0; i <= nl; ++i) { lf_ptr[i] = f_ptr[lo + i] - e0; lrc_ptr[i] = rc_ptr[lo + i] - k0; }
-        for (int32_t e = e0; e < e1; ++e) lmc_val[e - e0] = cval[f_slot[e]];
-        TRY(upload_long_rows(ctx, c, lf_ptr));
-        TRY(dev_upload(ctx, &c.f_ptr, lf_ptr));
-        TRY(dev_upload(ctx, &c.f_col, lf_col));
-        TRY(dev_upload(ctx, &c.mc_val, lmc_val));
-        TRY(dev_upload(ctx, &c.rc_ptr, lrc_ptr));
-        TRY(dev_upload(ctx, &c.rc_gid, lrc_gid));
-        TRY(dev_upload(ctx, &c.rc_a, lrc_a));
-        c.n = nl;
-        c.row_lo = lo;
-        c.n_alloc = rpr;
-        c.m_loc = k1 - k0;
-        c.nnzF = e1 - e0;
+        TRY(upload_long_rows(ctx, c, L.lf_ptr));
+        TRY(dev_upload(ctx, &c.f_ptr, L.lf_ptr));
+        TRY(dev_upload(ctx, &c.f_col, L.lf_col));
+        TRY(dev_upload(ctx, &c.mc_val, L.lmc_val));
+        TRY(dev_upload(ctx, &c.rc_ptr, L.lrc_ptr));
+        TRY(dev_upload(ctx, &c.rc_gid, L.lrc_gid));
+        TRY(dev_upload(ctx, &c.rc_a, L.lrc_a));
+        c.n = L.hi - L.lo;
+        c.row_lo = L.lo;
+        c.n_alloc = L.rows_per_rank;
+        c.m_loc = (int64_t)L.lrc_gid.size();
+        c.nnzF = (int64_t)L.lf_col.size();
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         return 0;
     }
+    const int64_t mA = L.mA, nnzP = L.nnzP;
     TRY(dev_upload(ctx, &c.pat_row, c.h_pat_row));
     TRY(dev_upload(ctx, &c.pat_col, c.h_pat_col));
-    TRY(dev_upload(ctx, &c.cval, cval));
-    TRY(dev_upload(ctx, &c.c_slot, c_slot));
-    TRY(dev_upload(ctx, &c.c_coef, c_coef));
-    TRY(dev_upload(ctx, &c.a_ptr, a_ptr));
-    TRY(dev_upload(ctx, &c.a_slot, a_slot));
-    TRY(dev_upload(ctx, &c.a_coef, a_coef));
-    TRY(dev_upload(ctx, &c.con_gid, con_gid));
+    TRY(dev_upload(ctx, &c.cval, L.cval));
+    TRY(dev_upload(ctx, &c.c_slot, L.c_slot));
+    TRY(dev_upload(ctx, &c.c_coef, L.c_coef));
+    TRY(dev_upload(ctx, &c.a_ptr, L.a_ptr));
+    TRY(dev_upload(ctx, &c.a_slot, L.a_slot));
+    TRY(dev_upload(ctx, &c.a_coef, L.a_coef));
+    TRY(dev_upload(ctx, &c.con_gid, L.con_gid));
     {
         /* lane group of the per-constraint gather from the average list length; lists far above it get their own CTA */
         c.con_group = pick_list_group(mA > 0 ? (double)c.nnzA / (double)mA : 0.0);
         std::vector<int32_t> lc;
         for (int64_t t = 0; t < mA; ++t)
-            if (a_ptr[t + 1] - a_ptr[t] > LGPU_LONG_ROW * c.con_group) lc.push_back((int32_t)t);
+            if (L.a_ptr[t + 1] - L.a_ptr[t] > LGPU_LONG_ROW * c.con_group) lc.push_back((int32_t)t);
         c.n_long_con = (int64_t)lc.size();
         if (!lc.empty()) TRY(dev_upload(ctx, &c.long_con, lc));
     }
-    TRY(dev_upload(ctx, &c.t_ptr, t_ptr));
-    TRY(dev_upload(ctx, &c.t_loc, t_loc));
-    TRY(dev_upload(ctx, &c.t_gid, t_gid));
-    TRY(dev_upload(ctx, &c.t_val, t_val));
-    TRY(upload_long_rows(ctx, c, f_ptr));
-    TRY(dev_upload(ctx, &c.f_ptr, f_ptr));
-    TRY(dev_upload(ctx, &c.f_col, f_col));
-    TRY(dev_upload(ctx, &c.f_slot, f_slot));
-    if (diag_only) {
-        TRY(dev_upload(ctx, &c.d_row, d_row));
-        TRY(dev_upload(ctx, &c.d_val, d_val));
-        /* fused path layout: C's value per full-CSR entry; row -> constraints, stable in constraint order */
-        std::vector<double> mc_val(c.nnzF);
-        for (int64_t e = 0; e < c.nnzF; ++e) mc_val[e] = cval[f_slot[e]];
-        std::vector<int32_t> rc_ptr(n + 1, 0), rc_gid(mA);
-        std::vector<double> rc_a(mA);
-        for (int64_t t = 0; t < mA; ++t) rc_ptr[d_row[t] + 1]++;
-        for (int64_t i = 0; i < n; ++i) rc_ptr[i + 1] += rc_ptr[i];
-        {
-            std::vector<int32_t> fill(rc_ptr.begin(), rc_ptr.end() - 1);
-            for (int64_t t = 0; t < mA; ++t) {
-                const int32_t q = fill[d_row[t]]++;
-                rc_gid[q] = con_gid[t];
-                rc_a[q] = d_val[t];
-            }
-        }
-        TRY(dev_upload(ctx, &c.mc_val, mc_val));
-        TRY(dev_upload(ctx, &c.rc_ptr, rc_ptr));
-        TRY(dev_upload(ctx, &c.rc_gid, rc_gid));
-        TRY(dev_upload(ctx, &c.rc_a, rc_a));
+    TRY(dev_upload(ctx, &c.t_ptr, L.t_ptr));
+    TRY(dev_upload(ctx, &c.t_loc, L.t_loc));
+    TRY(dev_upload(ctx, &c.t_gid, L.t_gid));
+    TRY(dev_upload(ctx, &c.t_val, L.t_val));
+    TRY(upload_long_rows(ctx, c, L.f_ptr));
+    TRY(dev_upload(ctx, &c.f_ptr, L.f_ptr));
+    TRY(dev_upload(ctx, &c.f_col, L.f_col));
+    TRY(dev_upload(ctx, &c.f_slot, L.f_slot));
+    if (L.diag_only) {
+        TRY(dev_upload(ctx, &c.d_row, L.d_row));
+        TRY(dev_upload(ctx, &c.d_val, L.d_val));
+        TRY(dev_upload(ctx, &c.mc_val, L.mc_val));
+        TRY(dev_upload(ctx, &c.rc_ptr, L.rc_ptr));
+        TRY(dev_upload(ctx, &c.rc_gid, L.rc_gid));
+        TRY(dev_upload(ctx, &c.rc_a, L.rc_a));
     }
     TRY(dev_alloc(ctx, &c.uvt, (size_t)nnzP));
     TRY(dev_alloc(ctx, &c.S, (size_t)nnzP));

@@ -91,6 +91,9 @@ def lib() -> ctypes.CDLL:
         "lgpu_lp_upload": (i, [_vp, _c_lp, _c_lp, _c_dp]),
         "lgpu_cone_info": (i, [_vp, i, _c_lp]),
         "lgpu_cone_classify": (i, [i64, i64, _c_lp, _c_lp, _c_lp]),
+        "lgpu_cone_layout_build": (i, [ctypes.POINTER(_vp), i64, i64, _c_lp, _c_lp, _c_dp, i, i]),
+        "lgpu_cone_layout_get": (i, [_vp, ctypes.c_char_p, i64, _vp, _c_lp, ctypes.POINTER(ctypes.c_int)]),
+        "lgpu_cone_layout_free": (None, [_vp]),
         "lgpu_cone_pattern": (i, [_vp, i, i64, _c_ip, _c_ip]),
         "lgpu_constants": (i, [_vp, _c_dp]),
         "lgpu_obj_scale": (i, [_vp, d]),
@@ -203,6 +206,38 @@ def cone_classify(p: "SdpaProblem", c: int) -> dict:
         raise LoradsError("lgpu_cone_classify failed")
     return dict(nnz_rows=int(o[0]), dense_aggregate=bool(o[1]), sparse_container=bool(o[2]), nnzP=int(o[3]),
                 diag_only=bool(o[4]), nnzA=int(o[5]))
+
+
+LAYOUT_ARRAYS = ("pat_row", "pat_col", "cval", "c_slot", "c_coef", "a_ptr", "a_slot", "a_coef", "con_gid", "t_ptr", "t_loc",
+                 "t_gid", "t_val", "f_ptr", "f_col", "f_slot", "d_row", "d_val", "mc_val", "rc_ptr", "rc_gid", "rc_a")
+LAYOUT_ARRAYS_PARTITIONED = ("lf_ptr", "lf_col", "lmc_val", "lrc_ptr", "lrc_gid", "lrc_a", "send_idx", "halo_gid", "send_off",
+                             "send_cnt", "recv_off", "recv_cnt")
+LAYOUT_SCALARS = ("mA", "nnzP", "nnzA", "nnzC", "nnzF", "max_con_len", "max_slot_len", "c_nrm1", "c_nrm2sq", "c_nrminf",
+                  "dense", "sparse_container", "diag_only", "use_halo", "halo_rows", "send_rows")
+
+
+def cone_layout(p: "SdpaProblem", c: int, names: Sequence[str], world: int = 1, rank: int = 0) -> dict:
+    """Device-layout arrays of cone c as lgpu_cone_upload builds them (lgpu_cone_layout_*): host code, no GPU."""
+    out = {}
+    L = lib()
+    h = _vp()
+    rc = L.lgpu_cone_layout_build(ctypes.byref(h), int(p.dims[c]), p.m, _i64(p.mat_beg[c]), _i64(p.mat_idx[c]),
+                                  p.mat_elem[c].ctypes.data_as(_c_dp), int(world), int(rank))
+    if rc != 0:
+        raise LoradsError(f"lgpu_cone_layout_build failed with {rc}")
+    try:
+        cnt, eb = ctypes.c_int64(), ctypes.c_int()
+        for nm in names:
+            rc = L.lgpu_cone_layout_get(h, nm.encode(), 0, None, ctypes.byref(cnt), ctypes.byref(eb))
+            if rc != 0:
+                raise LoradsError(f"lgpu_cone_layout_get({nm}) failed with {rc}")
+            a = np.zeros(cnt.value, dtype={4: np.int32, 8: np.float64, -8: np.int64}[eb.value])
+            if cnt.value:
+                L.lgpu_cone_layout_get(h, nm.encode(), a.nbytes, a.ctypes.data, ctypes.byref(cnt), ctypes.byref(eb))
+            out[nm] = dict(zip(LAYOUT_SCALARS, a.tolist())) if nm == "scalars" else a
+    finally:
+        L.lgpu_cone_layout_free(h)
+    return out
 
 
 def partition_rows(n: int, world: int, rank: int):
