@@ -2235,7 +2235,12 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
     DevCone &c = ctx->cones[cone];
     const int r = (int)c.r;
     const int nt = (r + 15) / 16;
+    /* enough (chunk, tile) units to fill the machine on small cones, 4096-row chunks on large ones */
     int64_t rows_per_chunk = 4096;
+    if (ctx->dense_dmma) {
+        const int64_t want = (c.n * nt * nt + (int64_t)ctx->num_sms * 8 - 1) / ((int64_t)ctx->num_sms * 8);
+        rows_per_chunk = std::min<int64_t>(4096, std::max<int64_t>(64, (want + 3) / 4 * 4));
+    }
     int nchunks = (int)((c.n + rows_per_chunk - 1) / rows_per_chunk);
     const size_t part_bytes = sizeof(double) * (size_t)nchunks * nt * nt * 256;
     const size_t gram_bytes = sizeof(double) * (size_t)r * r;
@@ -2245,7 +2250,14 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
     const double *A = (phase == 1 ? ctx->R : ctx->U) + c.off;
     const double *B = ctx->V + c.off;
     dim3 grid(nchunks, nt * nt);
-    {
+    if (ctx->dense_dmma) {
+        /* FP64 tensor pipe (DMMA), the default; lgpu_set_dense_tensor_path(0) selects the FMA kernel for A/B tests */
+        Prof pr(ctx, KC_DENSE);
+        const int64_t units = (int64_t)nchunks * nt * nt;
+        const int64_t blocks = std::min<int64_t>((units + 3) / 4, (int64_t)ctx->num_sms * 8); /* 4 warps per CTA */
+        k_gram_dmma<<<(unsigned)blocks, 128, 0, ctx->stream>>>(c.n, r, (int)c.ld, A, B, phase == 1 ? 0 : 1, rows_per_chunk, nchunks,
+                                                               part);
+    } else {
         Prof pr(ctx, KC_LAYOUT);
         k_gram_partial<<<grid, 256, 0, ctx->stream>>>(c.n, r, (int)c.ld, A, B, phase == 1 ? 0 : 1, rows_per_chunk, part);
     }

@@ -574,6 +574,57 @@ __global__ void __launch_bounds__(256) k_gram_partial(int64_t n, int r, int ld, 
     part[((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 256 + threadIdx.x] = acc;
 }
 
+/* K12 on the FP64 tensor pipe: one warp per (row chunk, 16 x 16 block of the Gram), 2 x 2 DMMA tiles, four factor rows per
+ * step.  With M the factor (or (A + B) / 2) the fragments are A[i][k] = M[row0 + k][i0 + i], B[k][j] = M[row0 + k][j0 + j],
+ * loaded straight from the row-major rows (8 consecutive doubles per row and fragment).  The warps of one chunk are
+ * neighbours in the grid, so the chunk's rows come from DRAM once and from L2 afterwards.  Partial blocks go to `part` in
+ * k_gram_partial's layout and k_gram_finish adds them in chunk order. */
+__global__ void __launch_bounds__(128) k_gram_dmma(int64_t n, int r, int ld, const double *__restrict__ A,
+                                                   const double *__restrict__ B, int average, int64_t rows_per_chunk,
+                                                   int nchunks, double *__restrict__ part)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nt = (r + 15) / 16, nt2 = nt * nt;
+    const int64_t units = (int64_t)nchunks * nt2;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < units; w += warps) {
+        const int tile = (int)(w % nt2);
+        const int64_t chunk = w / nt2;
+        const int ti = tile / nt, tj = tile % nt;
+        const int64_t r0 = chunk * rows_per_chunk;
+        const int64_t r1 = (r0 + rows_per_chunk < n) ? r0 + rows_per_chunk : n;
+        double c[2][2][2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) c[x][y][0] = c[x][y][1] = 0.0;
+        for (int64_t k0 = r0; k0 < r1; k0 += 4) {
+            const int64_t row = k0 + t;
+            double a[2], b[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int ca = ti * 16 + x * 8 + g, cb = tj * 16 + x * 8 + g;
+                a[x] = b[x] = 0.0;
+                if (row < r1) {
+                    if (ca < ld) a[x] = average ? 0.5 * (A[(size_t)row * ld + ca] + B[(size_t)row * ld + ca]) : A[(size_t)row * ld + ca];
+                    if (cb < ld) b[x] = average ? 0.5 * (A[(size_t)row * ld + cb] + B[(size_t)row * ld + cb]) : A[(size_t)row * ld + cb];
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x)
+#pragma unroll
+                for (int y = 0; y < 2; ++y) dmma_m8n8k4(c[x][y][0], c[x][y][1], a[x], b[y]);
+        }
+        double *dst = part + ((size_t)chunk * nt2 + tile) * 256;
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) dst[(x * 8 + g) * 16 + y * 8 + 2 * t + e] = c[x][y][e];
+    }
+}
+
 __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, int r, const double *__restrict__ part,
                                                      double *__restrict__ gram)
 {

@@ -322,6 +322,32 @@ def test_dense_cone_tensor_path(lb, tmp_path, n, r):
     assert rel(res[True][3], res[False][3]) < KTOL
 
 
+@pytest.mark.parametrize("n,r", [(37, 5), (800, 14), (3001, 33), (20000, 70)])
+def test_gram_tensor_path(lb, n, r):
+    """r x r Gram of the factor (oracle rank, build_gram_from_factor/_average, lorads_logging.c:216-270) on the FP64 tensor
+    pipe (DMMA) and with the FMA kernel, both against numpy; ranks that are not multiples of the 16-column block, row
+    counts that are not multiples of the 4-row step."""
+    ei, ej, w = lb.random_graph(n, 3, 1)
+    p = lb.maxcut_problem(n, ei, ej, w)
+    rng = np.random.default_rng(n + r)
+    R0, U0, V0 = (rng.normal(size=(n, r)) for _ in range(3))
+    res = {}
+    for tensor in (True, False):
+        ctx = lb.Context(0).load(p)
+        ctx.set_dense_tensor_path(tensor)
+        ctx.alloc_vars([r], 2)
+        ctx.set_factor(lb.R, 0, R0)
+        ctx.set_factor(lb.U, 0, U0)
+        ctx.set_factor(lb.V, 0, V0)
+        res[tensor] = (ctx.gram(1, 0), ctx.gram(2, 0))
+        ctx.close()
+    M = 0.5 * (U0 + V0)
+    for tensor in (True, False):
+        g1, g2 = res[tensor]
+        assert rel(g1, R0.T @ R0) < KTOL and rel(g2, M.T @ M) < KTOL
+        assert np.array_equal(g1, g1.T) or rel(g1, g1.T) < KTOL
+
+
 def test_hub_rows_long_row_kernel(lb, tmp_path):
     """A hub vertex (one CSR row of n - 1 entries, as in ice_2.0 / checker / p_auss) is handled by the one-CTA-per-row
     kernel: operator parity against the oracle and fused-vs-general agreement over ALM iterations."""
