@@ -276,6 +276,10 @@ int lorads_b200_main(int argc, char **argv)
     int nkids = 0;
     if (params.ranks > 64) params.ranks = 64;
     if (params.ranks > 1) {
+        /* the ranks read and preprocess at the same time: the reader and the layout builder divide the cores by this */
+        char nr[16];
+        snprintf(nr, sizeof(nr), "%d", params.ranks);
+        setenv("LORADS_LOCAL_RANKS", nr, 0);
         int fds[64][2];
         for (int r = 1; r < params.ranks; ++r)
             if (pipe(fds[r]) != 0) { perror("pipe"); return 3; }

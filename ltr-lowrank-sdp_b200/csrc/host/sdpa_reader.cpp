@@ -34,6 +34,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <thread>
 #include <vector>
 
@@ -379,6 +380,12 @@ int thread_count(size_t bytes)
     if (bytes < ((size_t)4 << 20)) return 1;
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     if (n < 1) n = 1;
+    /* the ranks of a multi-GPU run read at the same time and share the cores */
+    for (const char *name : {"LORADS_LOCAL_RANKS", "LOCAL_WORLD_SIZE"})
+        if (const char *s = getenv(name)) {
+            const int p = atoi(s);
+            if (p > 1) { n = std::max<long>(1, n / p); break; }
+        }
     return (int)std::min<long>(n, 32);
 }
 

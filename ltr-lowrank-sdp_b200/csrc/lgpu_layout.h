@@ -20,6 +20,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <initializer_list>
 #include <memory>
 #include <numeric>
 #include <string>
@@ -61,6 +62,13 @@ static int layout_threads(int64_t work)
     if (work < 200000) return 1;
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
+    /* one process per GPU: the ranks of a node preprocess at the same time and share the cores (LORADS_LOCAL_RANKS is set
+     * by the binary's --ranks, LOCAL_WORLD_SIZE by torchrun) */
+    for (const char *name : {"LORADS_LOCAL_RANKS", "LOCAL_WORLD_SIZE"})
+        if (const char *s = getenv(name)) {
+            const int p = atoi(s);
+            if (p > 1) { hw = std::max(1u, hw / (unsigned)p); break; }
+        }
     return (int)std::min<unsigned>(hw, 32u);
 }
 template <class F> static void par_run(int T, F f)
