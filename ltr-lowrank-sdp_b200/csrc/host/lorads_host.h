@@ -64,7 +64,9 @@ typedef struct {
     int64_t nElems;
 } lh_sdpa;
 
+/* reads SDPA sparse text (.dat-s) or, recognised by its magic, the binary image lh_write_sdpa_binary made of it */
 int lh_read_sdpa(const char *fname, lh_sdpa *out, int quiet);
+int lh_write_sdpa_binary(const char *fname, const lh_sdpa *d);
 void lh_free_sdpa(lh_sdpa *d);
 
 /* ---- phase states (reference: lorads_alm_state / lorads_admm_state, def_lorads_solver.h:198-238) */

@@ -339,6 +339,8 @@ int lorads_b200_main(int argc, char **argv)
     const double timeStart = lh_time();
     if (lh_read_sdpa(params.fname, &data, 0) != 0) return 0; /* the reference also exits with status 0 here */
     printf("Reading SDPA file in %f seconds \n", lh_time() - timeStart);
+    if (getenv("LORADS_SAVE_BINARY") && params.rank == 0 && lh_write_sdpa_binary(getenv("LORADS_SAVE_BINARY"), &data) != 0)
+        fprintf(stderr, "lorads_b200: cannot write the binary image '%s'\n", getenv("LORADS_SAVE_BINARY"));
     printf("nConstrs = %lld, sdp nBlks = %lld, lp Cols = %lld\n", (long long)data.m, (long long)data.nBlks,
            (long long)data.nLpCols);
 

@@ -389,7 +389,98 @@ int thread_count(size_t bytes)
     return (int)std::min<long>(n, 32);
 }
 
+/* ---- binary side channel ---------------------------------------------------------------------------------------
+ * The parsed problem, array for array (the text of a C5-size instance is ~1.8 GB; .dat-s stays the canonical
+ * format, this is a cache of what reading it produced).  Little-endian, 8-byte fields:
+ *   magic "LORADSB1" | m nBlks nLpCols nElems | blkDims[nBlks] | b[m] | per block: beg[m+2] idx[N] val[N] | LP: beg[m+2] idx val */
+const char kBinaryMagic[8] = {'L', 'O', 'R', 'A', 'D', 'S', 'B', '1'};
+
+template <class T> bool take(const char *&p, const char *end, T *dst, int64_t count)
+{
+    if (count < 0 || (uint64_t)(end - p) < (uint64_t)count * sizeof(T)) return false;
+    /* big arrays: copied by several threads */
+    const int T2 = (count * (int64_t)sizeof(T) > ((int64_t)64 << 20)) ? thread_count((size_t)count * sizeof(T)) : 1;
+    const char *src = p;
+    run_threads(T2, [&](int t) {
+        const int64_t lo = count * t / T2, hi = count * (t + 1) / T2;
+        memcpy(dst + lo, src + lo * sizeof(T), (size_t)(hi - lo) * sizeof(T));
+    });
+    p += count * sizeof(T);
+    return true;
+}
+
+int read_csc(const char *&p, const char *end, int64_t m, int64_t **beg, int64_t **idx, double **val)
+{
+    *beg = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 2));
+    if (!*beg || !take(p, end, *beg, m + 2)) return 1;
+    const int64_t N = (*beg)[m + 1];
+    if (N < 0 || (*beg)[0] != 0) return 1;
+    for (int64_t c = 0; c <= m; ++c)
+        if ((*beg)[c + 1] < (*beg)[c]) return 1;
+    *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(N > 0 ? N : 1));
+    *val = (double *)malloc(sizeof(double) * (size_t)(N > 0 ? N : 1));
+    if (!*idx || !*val || !take(p, end, *idx, N) || !take(p, end, *val, N)) return 1;
+    return 0;
+}
+
+int read_binary(const char *buf, size_t sz, lh_sdpa *out)
+{
+    const char *p = buf + sizeof(kBinaryMagic), *end = buf + sz;
+    int64_t head[4];
+    if (!take(p, end, head, 4)) return 1;
+    const int64_t m = head[0], nb = head[1], nlp = head[2];
+    if (m <= 0 || nb < 0 || nlp < 0 || nb > (int64_t)1 << 40) return 1;
+    out->m = m; out->nBlks = nb; out->nLpCols = nlp; out->nElems = head[3];
+    const size_t nbs = (size_t)(nb > 0 ? nb : 1);
+    out->blkDims = (int64_t *)malloc(sizeof(int64_t) * nbs);
+    out->b = (double *)malloc(sizeof(double) * (size_t)m);
+    out->matBeg = (int64_t **)calloc(nbs, sizeof(int64_t *));
+    out->matIdx = (int64_t **)calloc(nbs, sizeof(int64_t *));
+    out->matElem = (double **)calloc(nbs, sizeof(double *));
+    if (!out->blkDims || !out->b || !out->matBeg || !out->matIdx || !out->matElem) return 1;
+    if (!take(p, end, out->blkDims, nb) || !take(p, end, out->b, m)) return 1;
+    for (int64_t k = 0; k < nb; ++k) {
+        if (out->blkDims[k] <= 0) return 1;
+        if (read_csc(p, end, m, &out->matBeg[k], &out->matIdx[k], &out->matElem[k])) return 1;
+        const int64_t tri = out->blkDims[k] * (out->blkDims[k] + 1) / 2, N = out->matBeg[k][m + 1];
+        for (int64_t e = 0; e < N; ++e)
+            if (out->matIdx[k][e] < 0 || out->matIdx[k][e] >= tri) return 1;
+    }
+    if (nlp > 0) {
+        if (read_csc(p, end, m, &out->lpBeg, &out->lpIdx, &out->lpElem)) return 1;
+        for (int64_t e = 0; e < out->lpBeg[m + 1]; ++e)
+            if (out->lpIdx[e] < 0 || out->lpIdx[e] >= nlp) return 1;
+    }
+    return p == end ? 0 : 1;
+}
+
 } // namespace
+
+extern "C" int lh_write_sdpa_binary(const char *fname, const lh_sdpa *d)
+{
+    FILE *f = fopen(fname, "wb");
+    if (!f) return 1;
+    bool ok = fwrite(kBinaryMagic, 1, sizeof(kBinaryMagic), f) == sizeof(kBinaryMagic);
+    auto put = [&](const void *src, size_t bytes) { if (ok && bytes > 0) ok = fwrite(src, 1, bytes, f) == bytes; };
+    const int64_t head[4] = {d->m, d->nBlks, d->nLpCols, d->nElems};
+    put(head, sizeof(head));
+    put(d->blkDims, sizeof(int64_t) * (size_t)d->nBlks);
+    put(d->b, sizeof(double) * (size_t)d->m);
+    for (int64_t k = 0; k < d->nBlks; ++k) {
+        const int64_t N = d->matBeg[k][d->m + 1];
+        put(d->matBeg[k], sizeof(int64_t) * (size_t)(d->m + 2));
+        put(d->matIdx[k], sizeof(int64_t) * (size_t)N);
+        put(d->matElem[k], sizeof(double) * (size_t)N);
+    }
+    if (d->nLpCols > 0) {
+        const int64_t N = d->lpBeg[d->m + 1];
+        put(d->lpBeg, sizeof(int64_t) * (size_t)(d->m + 2));
+        put(d->lpIdx, sizeof(int64_t) * (size_t)N);
+        put(d->lpElem, sizeof(double) * (size_t)N);
+    }
+    if (fclose(f) != 0) ok = false;
+    return ok ? 0 : 1;
+}
 
 extern "C" int lh_read_sdpa(const char *fname, lh_sdpa *out, int quiet)
 {
@@ -404,6 +495,12 @@ extern "C" int lh_read_sdpa(const char *fname, lh_sdpa *out, int quiet)
     close(fd);
     if (buf == MAP_FAILED) return 1;
     madvise((void *)buf, sz, MADV_WILLNEED);
+    if (sz >= sizeof(kBinaryMagic) && memcmp(buf, kBinaryMagic, sizeof(kBinaryMagic)) == 0) {
+        const int brc = read_binary(buf, sz, out);
+        munmap((void *)buf, sz);
+        if (brc) lh_free_sdpa(out);
+        return brc;
+    }
     const char *p = buf, *end = buf + sz;
     int rc = 1;
     Shape sh;

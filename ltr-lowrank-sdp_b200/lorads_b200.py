@@ -160,6 +160,8 @@ def host_lib() -> ctypes.CDLL:
     H = ctypes.CDLL(HOST_LIB_PATH)
     H.lh_read_sdpa.restype = ctypes.c_int
     H.lh_read_sdpa.argtypes = [ctypes.c_char_p, ctypes.POINTER(_Sdpa), ctypes.c_int]
+    H.lh_write_sdpa_binary.restype = ctypes.c_int
+    H.lh_write_sdpa_binary.argtypes = [ctypes.c_char_p, ctypes.POINTER(_Sdpa)]
     H.lh_free_sdpa.restype = None
     H.lh_free_sdpa.argtypes = [ctypes.POINTER(_Sdpa)]
     H.lh_cubic_equation.restype = ctypes.c_int
@@ -281,6 +283,26 @@ def read_sdpa(path: str) -> SdpaProblem:
         return SdpaProblem(m, dims, b, begs, idxs, elems, nlp, lp_beg, lp_idx, lp_elem)
     finally:
         H.lh_free_sdpa(ctypes.byref(s))
+
+
+def write_sdpa_binary(path: str, p: SdpaProblem) -> None:
+    """The binary image of a problem (lh_write_sdpa_binary): what reading the .dat-s text produces, array for array.
+    The binary accepts it wherever it accepts a .dat-s file (recognised by its magic)."""
+    H = host_lib()
+    s = _Sdpa()
+    nb = p.ncones
+    s.m, s.nBlks, s.nLpCols = p.m, nb, p.nlp
+    s.nElems = int(sum(int(b[-1]) for b in p.mat_beg) + (int(p.lp_beg[-1]) if p.nlp else 0))
+    s.blkDims = _i64(p.dims)
+    s.b = p.b.ctypes.data_as(_c_dp)
+    begs = (_c_lp * max(nb, 1))(*[_i64(a) for a in p.mat_beg])
+    idxs = (_c_lp * max(nb, 1))(*[_i64(a) for a in p.mat_idx])
+    vals = (_c_dp * max(nb, 1))(*[a.ctypes.data_as(_c_dp) for a in p.mat_elem])
+    s.matBeg, s.matIdx, s.matElem = begs, idxs, vals
+    if p.nlp:
+        s.lpBeg, s.lpIdx, s.lpElem = _i64(p.lp_beg), _i64(p.lp_idx), p.lp_elem.ctypes.data_as(_c_dp)
+    if H.lh_write_sdpa_binary(os.fsencode(path), ctypes.byref(s)) != 0:
+        raise LoradsError(f"cannot write {path}")
 
 
 def run_solver(argv: Sequence[str], **kw) -> subprocess.CompletedProcess:

@@ -319,3 +319,30 @@ def test_reader_number_conversion_is_strtod(built, tmp_path, monkeypatch):
         beg = p.mat_beg[0]
         keep = [float(t) for t in toks if abs(float(t)) >= 1e-12]
         assert p.mat_elem[0][beg[1]:beg[2]].tobytes() == np.array(keep).tobytes()
+
+
+@pytest.mark.parametrize("name", ["G11", "multiblock_lp", "theta_n30"])
+def test_binary_image_round_trip(built, tmp_path, name):
+    """SURVEY 8d side channel: the binary image of a parsed problem reads back array for array; a damaged or truncated
+    image is refused, never half-read."""
+    lb = built
+    p = lb.read_sdpa(inst_path(name))
+    f = tmp_path / "img.lbin"
+    lb.write_sdpa_binary(str(f), p)
+    q = lb.read_sdpa(str(f))
+    assert q.m == p.m and list(q.dims) == list(p.dims) and q.nlp == p.nlp and np.array_equal(q.b, p.b)
+    for k in range(p.ncones):
+        assert np.array_equal(q.mat_beg[k], p.mat_beg[k]) and np.array_equal(q.mat_idx[k], p.mat_idx[k])
+        assert q.mat_elem[k].tobytes() == p.mat_elem[k].tobytes()
+    if p.nlp:
+        assert np.array_equal(q.lp_beg, p.lp_beg) and np.array_equal(q.lp_idx, p.lp_idx) and np.array_equal(q.lp_elem, p.lp_elem)
+    raw = f.read_bytes()
+    (tmp_path / "short.lbin").write_bytes(raw[:-9])
+    (tmp_path / "long.lbin").write_bytes(raw + b"\0" * 8)
+    bad = bytearray(raw)
+    off = 8 + 32 + 8 * p.ncones + 8 * p.m + 8 * (p.m + 2)   # first packed index of block 0
+    bad[off:off + 8] = (2 ** 40).to_bytes(8, "little")
+    (tmp_path / "bad.lbin").write_bytes(bytes(bad))
+    for nm in ("short.lbin", "long.lbin", "bad.lbin"):
+        with pytest.raises(lb.LoradsError):
+            lb.read_sdpa(str(tmp_path / nm))
