@@ -346,3 +346,45 @@ def test_binary_image_round_trip(built, tmp_path, name):
     for nm in ("short.lbin", "long.lbin", "bad.lbin"):
         with pytest.raises(lb.LoradsError):
             lb.read_sdpa(str(tmp_path / nm))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_reader_layout_variations(built, tmp_path, monkeypatch, seed):
+    """Text-layout variations the reference's per-line sscanf accepts: CRLF line ends, blank lines, leading blanks, extra
+    tokens after the value, no newline at the end of the file, a comment block after the entries -- for several thread
+    counts, so that piece boundaries fall inside all of them."""
+    rng = np.random.default_rng(1000 + seed)
+    m, dims, nlp = 5, [30, 7], (4 if seed % 2 else 0)
+    text, want = _random_sdpa_text(rng, m, dims, nlp, count=3000)
+    head, body = text.split("\n", 5)[:5], text.split("\n", 5)[5]
+    lines = body.rstrip("\n").split("\n")
+    out = []
+    for k, ln in enumerate(lines):
+        ln = ln.rstrip("\r")
+        if k % 7 == 0:
+            ln = "   " + ln
+        if k % 5 == 0:
+            ln = ln + "  trailing 1 2 3"
+        out.append(ln)
+        if k % 13 == 0:
+            out.append("")
+    eol = "\r\n" if seed % 3 == 0 else "\n"
+    text2 = "\n".join(head) + "\n" + eol.join(out)
+    if seed % 2 == 0:
+        text2 += eol + "BEGIN.COMMENT" + eol + "1 1 1 1 99.0" + eol
+    f = tmp_path / "var.dat-s"
+    f.write_bytes(text2.encode())
+    ref = None
+    for thr in ("1", "3", "8"):
+        monkeypatch.setenv("LORADS_READ_THREADS", thr)
+        p = built.read_sdpa(str(f))
+        got = ([a.tobytes() for a in p.mat_beg + p.mat_idx + p.mat_elem], None if not nlp else
+               (p.lp_beg.tobytes(), p.lp_idx.tobytes(), p.lp_elem.tobytes()))
+        if ref is None:
+            ref = got
+            total = sum(int(b[-1]) for b in p.mat_beg) + (int(p.lp_beg[-1]) if nlp else 0)
+            assert total == len(want)          # nothing dropped, nothing read from the comment block
+            vals = np.sort(np.concatenate(p.mat_elem + ([p.lp_elem] if nlp else [])))
+            assert vals.tobytes() == np.sort(np.array([w[4] for w in want])).tobytes()
+        else:
+            assert got == ref, thr
