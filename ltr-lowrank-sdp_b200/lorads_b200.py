@@ -258,7 +258,7 @@ def nccl_unique_id() -> bytes:
 
 
 def read_sdpa(path: str) -> SdpaProblem:
-    """Parse a .dat-s file with the C host reader (csrc/host/sdpa_reader.c)."""
+    """Parse a .dat-s file (or its binary image) with the host reader (csrc/host/sdpa_reader.cpp)."""
     H = host_lib()
     s = _Sdpa()
     if H.lh_read_sdpa(os.fsencode(path), ctypes.byref(s), 1) != 0:
