@@ -12,7 +12,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 DATA = os.path.join(ROOT, "bench_data")
 sys.path.insert(0, os.path.join(ROOT, "ltr-lowrank-sdp_b200"))
 
