@@ -114,6 +114,89 @@ int lh_sym_eigvals(int n, double *a, double *w)
     return 0;
 }
 
+/* Number of eigenvalues of the symmetric n x n matrix a (row-major, destroyed) above eps * lambda_max -- all the oracle
+ * rank needs (lorads_compute_oracle_rank, lorads_logging.c:503-543, calls dsyevr for the whole spectrum).  Householder
+ * reduction to tridiagonal form, then Sturm counts: lambda_max by bisection, the rank as n - #{lambda <= cut}.  O(n^3)
+ * with a small constant instead of the cyclic Jacobi sweeps of lh_sym_eigvals (93 ms -> ~3 ms at n = 158); returns -1
+ * if lambda_max <= 0 (rank 0 by the reference's rule). */
+static int sturm_count_below(int n, const double *d, const double *e2, double x, double tiny)
+{
+    /* number of eigenvalues of tridiag(d, e) that are < x: negative pivots of the LDL^T of T - x I */
+    int cnt = 0;
+    double q = 1.0;
+    for (int i = 0; i < n; ++i) {
+        q = d[i] - x - (i > 0 ? e2[i - 1] / q : 0.0);
+        if (fabs(q) < tiny) q = -tiny;
+        if (q < 0.0) ++cnt;
+    }
+    return cnt;
+}
+
+int64_t lh_sym_rank(int n, double *a, double eps)
+{
+    if (n <= 0) return 0;
+    double *d = (double *)malloc(sizeof(double) * (size_t)n * 4);
+    if (!d) return -1;
+    double *e2 = d + n, *v = e2 + n, *p = v + n;
+    /* Householder: after step k, row/column k is (.., e[k-1], d[k], e[k], 0, ..) */
+    for (int k = 0; k + 2 < n; ++k) {
+        double scale = 0.0;
+        for (int i = k + 1; i < n; ++i) scale = fmax(scale, fabs(a[i * n + k]));
+        d[k] = a[k * n + k];
+        if (scale == 0.0) { e2[k] = 0.0; continue; }
+        double nrm2 = 0.0;
+        for (int i = k + 1; i < n; ++i) { v[i] = a[i * n + k] / scale; nrm2 += v[i] * v[i]; }
+        const double alpha = (v[k + 1] >= 0.0 ? -1.0 : 1.0) * sqrt(nrm2);
+        e2[k] = (alpha * scale) * (alpha * scale);
+        v[k + 1] -= alpha;
+        const double vtv = nrm2 - 2.0 * alpha * (v[k + 1] + alpha) + alpha * alpha; /* |v|^2 after the shift */
+        if (vtv == 0.0) continue;
+        /* B <- H B H on the trailing block, H = I - 2 v v^T / (v^T v):  B - v q^T - q v^T,  q = p - (v^T p / v^T v) v */
+        double vtp = 0.0;
+        for (int i = k + 1; i < n; ++i) {
+            double t = 0.0;
+            for (int j = k + 1; j < n; ++j) t += a[i * n + j] * v[j];
+            p[i] = 2.0 * t / vtv;
+            vtp += v[i] * p[i];
+        }
+        const double kk = vtp / vtv;
+        for (int i = k + 1; i < n; ++i) p[i] -= kk * v[i];
+        for (int i = k + 1; i < n; ++i)
+            for (int j = k + 1; j < n; ++j) a[i * n + j] -= v[i] * p[j] + p[i] * v[j];
+    }
+    if (n >= 2) {
+        d[n - 2] = a[(n - 2) * n + (n - 2)];
+        e2[n - 2] = a[(n - 1) * n + (n - 2)] * a[(n - 1) * n + (n - 2)];
+    }
+    d[n - 1] = a[(n - 1) * n + (n - 1)];
+    /* Gershgorin interval, then lambda_max by bisection on the Sturm count */
+    double lo = d[0], hi = d[0];
+    for (int i = 0; i < n; ++i) {
+        const double r = (i > 0 ? sqrt(e2[i - 1]) : 0.0) + (i + 1 < n ? sqrt(e2[i]) : 0.0);
+        lo = fmin(lo, d[i] - r);
+        hi = fmax(hi, d[i] + r);
+    }
+    const double span = fmax(fabs(lo), fabs(hi));
+    const double tiny = fmax(span * 1e-30, 1e-300); /* a pivot this small is taken as negative (as in LAPACK's dstebz) */
+    double a0 = lo, b0 = hi;
+    for (int it = 0; it < 200 && b0 - a0 > 4e-16 * fmax(fabs(a0), fabs(b0)); ++it) {
+        const double mid = 0.5 * (a0 + b0);
+        if (mid <= a0 || mid >= b0) break;
+        if (sturm_count_below(n, d, e2, mid, tiny) >= n) b0 = mid; /* all eigenvalues < mid */
+        else a0 = mid;
+    }
+    const double lmax = 0.5 * (a0 + b0);
+    int64_t rk = -1;
+    if (lmax > 0.0) {
+        /* eigenvalues > cut  =  n - #{lambda < cut} - #{lambda == cut}; equality has measure zero, the count just above
+         * the cut is what dsyevr's rounded eigenvalues would give as well */
+        const double cut = eps * lmax;
+        rk = n - sturm_count_below(n, d, e2, nextafter(cut, INFINITY), tiny);
+    }
+    free(d);
+    return rk;
+}
+
 int64_t lh_oracle_rank(lh_solver *S, int phase)
 {
     if (S->disableOracle) return 0;
@@ -122,21 +205,14 @@ int64_t lh_oracle_rank(lh_solver *S, int phase)
     for (int64_t c = 0; c < S->nCones; ++c) {
         const int r = (int)S->rank[c];
         double *g = (double *)malloc(sizeof(double) * (size_t)r * r);
-        double *w = (double *)malloc(sizeof(double) * (size_t)r);
-        if (!g || !w || lgpu_gram(S->gpu, phase, (int)c, g) != 0) {
-            free(g); free(w);
+        if (!g || lgpu_gram(S->gpu, phase, (int)c, g) != 0) {
+            free(g);
             return -1;
         }
-        lh_sym_eigvals(r, g, w);
-        const double lmax = w[r - 1];
-        int64_t rk = 0;
-        if (lmax > 0) {
-            const double cut = eps * lmax;
-            for (int i = 0; i < r; ++i)
-                if (w[i] > cut) rk++;
-        }
+        int64_t rk = lh_sym_rank(r, g, eps);
+        if (rk < 0) rk = 0; /* lambda_max <= 0: rank 0 (lorads_logging.c:535-541) */
         total += rk;
-        free(g); free(w);
+        free(g);
     }
     return total;
 }

@@ -162,6 +162,7 @@ void lh_append_trajectory(lh_solver *S, int phase, int64_t cur_rank, int64_t ora
 void lh_write_json(lh_solver *S, int64_t final_oracle_rank, double pobj, double dobj, double l1, double linf, double gap,
                    double solve_time, double rho_max, double heuristic_factor);
 int lh_sym_eigvals(int n, double *a, double *w); /* Jacobi; a is destroyed */
+int64_t lh_sym_rank(int n, double *a, double eps);
 
 /* whole program: what `main` of the reference binary does (main.c:256-645); returns the process exit code */
 int lorads_b200_main(int argc, char **argv);

@@ -389,3 +389,38 @@ def test_reader_layout_variations(built, tmp_path, monkeypatch, seed):
             assert vals.tobytes() == np.sort(np.array([w[4] for w in want])).tobytes()
         else:
             assert got == ref, thr
+
+
+def test_oracle_rank_count_matches_dense_eigenvalues(built):
+    """lh_sym_rank (Householder + Sturm counts) = #{eigenvalues > 1e-6 lambda_max}, the reference's oracle-rank rule
+    (lorads_logging.c:503-543), on full-rank, low-rank + noise, threshold-straddling, diagonal, zero and negative
+    matrices; a disagreement is accepted only when an eigenvalue sits on the cut to 1e-7 relative."""
+    H = built.host_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    H.lh_sym_rank.restype = ctypes.c_int64
+    H.lh_sym_rank.argtypes = [ctypes.c_int, dp, ctypes.c_double]
+    rng = np.random.default_rng(0)
+    for trial in range(800):
+        n = int(rng.integers(1, 60)) if trial % 50 else int(rng.integers(150, 280))
+        k = int(rng.integers(0, n + 1))
+        kind = trial % 5
+        if kind == 0:
+            A = rng.normal(size=(n + 3, n))
+            G = A.T @ A
+        elif kind == 1:
+            A = rng.normal(size=(n, k))
+            G = A @ A.T + 1e-9 * np.eye(n) * rng.random()
+        elif kind == 2:
+            Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+            G = (Q * 10.0 ** rng.uniform(-10, 2, size=n)) @ Q.T
+        elif kind == 3:
+            G = np.diag(rng.random(n) * (rng.random(n) > 0.5))
+        else:
+            G = -np.eye(n) * rng.random() if trial % 2 else np.zeros((n, n))
+        G = np.ascontiguousarray(0.5 * (G + G.T))
+        w = np.linalg.eigvalsh(G)
+        want = int(np.sum(w > 1e-6 * w[-1])) if w[-1] > 0 else -1
+        got = H.lh_sym_rank(n, G.copy().ctypes.data_as(dp), 1e-6)
+        if got != want:
+            cut = 1e-6 * w[-1]
+            assert np.min(np.abs(w - cut)) <= 1e-7 * abs(cut) + 1e-14 * abs(w[-1]), (trial, n, kind, got, want)
