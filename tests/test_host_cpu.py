@@ -424,3 +424,15 @@ def test_oracle_rank_count_matches_dense_eigenvalues(built):
         if got != want:
             cut = 1e-6 * w[-1]
             assert np.min(np.abs(w - cut)) <= 1e-7 * abs(cut) + 1e-14 * abs(w[-1]), (trial, n, kind, got, want)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/lorads_b200.h is the drop-in boundary: it must compile on its own as C99 and as C++ (no torch types, no
+    CUDA headers), so a maintainer can include it from the reference's C sources."""
+    hdr = os.path.join(ROOT, "include", "lorads_b200.h")
+    for cc, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")):
+        src = tmp_path / f"inc.{ext}"
+        src.write_text('#include "lorads_b200.h"\nint main(void) { return lgpu_version() == 0; }\n')
+        r = subprocess.run([cc, std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
