@@ -220,3 +220,32 @@ def test_partitioned_layout_rejects_general_cones(built):
     p = _random_problem(built, rng, n=60, m=40, per_con=3, nobj=50, shuffle=False)
     with pytest.raises(built.LoradsError):
         built.cone_layout(p, 0, ["f_ptr"], world=2, rank=0)
+
+
+@pytest.mark.parametrize("graph,world", [("torus", 2), ("torus", 4), ("random", 3), ("random", 8)])
+def test_halo_plan_is_consistent_across_ranks(built, monkeypatch, graph, world):
+    """What rank p packs for rank q must be, row for row and in the same order, what q expects to receive from p: the
+    two sides derive their lists independently (each from the whole CSR) and never talk about them."""
+    lb = built
+    monkeypatch.setenv("LORADS_HALO", "1")
+    n = 1200
+    ei, ej, w = lb.torus_graph(30, 40, 5) if graph == "torus" else lb.random_graph(n, 4, 5)
+    p = lb.maxcut_problem(n, ei, ej, w)
+    L = [lb.cone_layout(p, 0, ["send_idx", "send_off", "send_cnt", "recv_off", "recv_cnt", "halo_gid", "lf_col", "lf_ptr"], world, r)
+         for r in range(world)]
+    lo = [lb.partition_rows(n, world, r)[0] for r in range(world)]
+    rpr = lb.partition_rows(n, world, 0)[2]
+    for src in range(world):
+        for dst in range(world):
+            if src == dst:
+                assert L[src]["send_cnt"][dst] == 0 and L[dst]["recv_cnt"][src] == 0
+                continue
+            s0, sc = int(L[src]["send_off"][dst]), int(L[src]["send_cnt"][dst])
+            r0, rc = int(L[dst]["recv_off"][src]), int(L[dst]["recv_cnt"][src])
+            assert sc == rc
+            assert np.array_equal(L[src]["send_idx"][s0:s0 + sc].astype(np.int64) + lo[src], L[dst]["halo_gid"][r0:r0 + rc])
+    # every remapped column is an own row or a halo row that exists
+    for r in range(world):
+        nl = len(L[r]["lf_ptr"]) - 1
+        cols = L[r]["lf_col"]
+        assert np.all((cols < nl) | ((cols >= rpr) & (cols < rpr + len(L[r]["halo_gid"]))))
