@@ -207,6 +207,11 @@ int lgpu_partition_rows(int64_t n, int world, int rank, int64_t *lo, int64_t *hi
 /* ncclUniqueId is 128 bytes; rank 0 calls lgpu_nccl_unique_id and the host side distributes it to the other ranks */
 int lgpu_nccl_unique_id(unsigned char id[128]);
 int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int rank, int world);
+/* Collective yes/no decision for anything a rank derives from its OWN clock or environment (the reference's
+ * wall-clock tests against timeSecLimit, lorads_alm.c:1441, lorads_admm.c:170-173, main.c:471,519,583): on return
+ * *flag is rank 0's value on every rank (rank 0 is authoritative), so all ranks leave a loop in the same iteration
+ * and nobody is left waiting inside the next collective.  One GPU: *flag is returned unchanged. */
+int lgpu_agree_flag(lgpu_ctx *ctx, int *flag);
 
 #ifdef __cplusplus
 }

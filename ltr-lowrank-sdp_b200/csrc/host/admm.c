@@ -154,7 +154,7 @@ static int admm_loop(lh_params *p, lh_solver *S, lh_admm_state *st, int64_t iter
         if (st->iter % 50 == 0) {
             if (dimacs_admm(S)) return LH_RET_DEVICE;
             take_errors(S, st, 0);
-            if (lh_time() - timeSolveStart >= p->timeSecLimit) return LH_RET_TIME_OUT;
+            if (lh_time_is_up(S, p, timeSolveStart, 0)) return LH_RET_TIME_OUT;
         }
         if (st->primal_dual_gap <= p->phase2Tol * 1e-3 && st->l_1_primal_infeasibility <= p->phase2Tol * 1e-3) {
             lh_log(S, "Early Stop When DIMACS Errors Are Well-Satisfied\n");

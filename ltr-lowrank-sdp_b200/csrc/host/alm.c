@@ -304,7 +304,7 @@ int lh_alm_optimize(lh_params *p, lh_solver *S, lh_alm_state *st, double timeSol
                 break;
             }
             alm_record(S, st, lh_time() - t_begin);
-            if (lh_time() - timeSolveStart >= p->timeSecLimit) { goto_print = 1; break; }
+            if (lh_time_is_up(S, p, timeSolveStart, 0)) { goto_print = 1; break; }
             if ((double)rank_flag >= rank_flag_thres && !is_rank_max) {
                 rank_flag = 0;
                 if (k - last_start >= 2) {
@@ -436,7 +436,7 @@ int lh_alm_optimize_reopt(lh_params *p, lh_solver *S, lh_alm_state *st, int earl
                 if (st->primal_dual_gap <= p->phase2Tol && st->l_1_primal_infeasibility <= p->phase2Tol && (k - k0) > 1) { goto_print = 1; break; }
             }
             alm_record(S, st, lh_time() - t_begin);
-            if (lh_time() - timeSolveStart >= p->timeSecLimit) { goto_print = 1; break; }
+            if (lh_time_is_up(S, p, timeSolveStart, 0)) { goto_print = 1; break; }
             if ((double)rank_flag >= rank_flag_thres && !is_rank_max && S->nCones <= 10) {
                 rank_flag = 0;
                 if (k - last_start >= 2) {

@@ -121,6 +121,9 @@ typedef struct {
 } lh_solver;
 
 double lh_time(void);
+/* the reference's `time - timeSolveStart >= timeSecLimit` tests, made collective: in a --ranks P run every rank reads
+ * its own clock, so the decision is rank 0's, distributed through the communicator (lgpu_agree_flag) */
+int lh_time_is_up(lh_solver *S, const lh_params *p, double timeSolveStart, int strict);
 
 /* glibc_rand.c: glibc's srand()/rand() value stream, lock-free */
 void lh_srand(unsigned int seed);

@@ -381,7 +381,7 @@ int lorads_b200_main(int argc, char **argv)
     double time_start = lh_time(), time_end;
     rc = lh_alm_optimize(&params, S, &alm, timeSolveStart);
     if (rc == LH_RET_DEVICE) { exit_code = 3; goto close_log; }
-    if (lh_time() - timeSolveStart > params.timeSecLimit) {
+    if (lh_time_is_up(S, &params, timeSolveStart, 1)) {
         printf("Time limit reached\n");
         S->status = LH_STATUS_TIME_LIMIT;
         goto end_solving;
@@ -406,7 +406,7 @@ int lorads_b200_main(int argc, char **argv)
             time_end = lh_time();
             all_time += (time_end - time_start);
             cnt += 1;
-            if (lh_time() - timeSolveStart > params.timeSecLimit) {
+            if (lh_time_is_up(S, &params, timeSolveStart, 1)) {
                 printf("Time limit reached\n");
                 S->status = LH_STATUS_TIME_LIMIT;
                 goto end_solving;
@@ -450,7 +450,7 @@ int lorads_b200_main(int argc, char **argv)
                    admm.l_inf_dual_infeasibility, admm.l_2_dual_infeasibility);
             printf("-----------------------------------------------------------------------\n");
             dual_cnt += 1;
-            if (lh_time() - timeSolveStart > params.timeSecLimit) {
+            if (lh_time_is_up(S, &params, timeSolveStart, 1)) {
                 printf("Time limit reached\n");
                 S->status = LH_STATUS_TIME_LIMIT;
                 goto end_solving;

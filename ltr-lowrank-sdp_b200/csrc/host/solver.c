@@ -21,6 +21,15 @@ double lh_time(void)
     return (double)tv.tv_sec + (double)tv.tv_usec * 1e-6;
 }
 
+int lh_time_is_up(lh_solver *S, const lh_params *p, double timeSolveStart, int strict)
+{
+    const double el = lh_time() - timeSolveStart;
+    int up = strict ? (el > p->timeSecLimit) : (el >= p->timeSecLimit);
+    if (S->gpu != NULL && lgpu_agree_flag(S->gpu, &up) != 0)
+        fprintf(stderr, "lorads_b200: device error: %s\n", lgpu_last_error(S->gpu));
+    return up;
+}
+
 #define GPU_TRY(S, call)                                                                   \
     do {                                                                                   \
         if ((call) != 0) {                                                                 \

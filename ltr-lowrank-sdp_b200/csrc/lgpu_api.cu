@@ -28,6 +28,7 @@
         char _buf[512];                                       \
         snprintf(_buf, sizeof(_buf), __VA_ARGS__);            \
         (ctx)->err = _buf;                                    \
+        (ctx)->failed = true;                                 \
         return 1;                                             \
     } while (0)
 
@@ -37,8 +38,11 @@
         if (_e != cudaSuccess) LGPU_FAIL(ctx, "%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
     } while (0)
 
+/* also trips on a sticky earlier failure (an NCCL call inside a void helper): the solver must not continue on
+ * per-rank partial sums or a stale product */
 #define CHECK_LAUNCH(ctx)                                                                                  \
     do {                                                                                                   \
+        if ((ctx)->failed) return 1;                                                                       \
         cudaError_t _e = cudaGetLastError();                                                               \
         if (_e != cudaSuccess) LGPU_FAIL(ctx, "%s:%d kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
     } while (0)
@@ -310,6 +314,19 @@ extern "C" int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int ra
     return 0;
 }
 
+extern "C" int lgpu_agree_flag(lgpu_ctx *ctx, int *flag)
+{
+    if (!ctx || !flag) return 1;
+    if (ctx->world <= 1) return 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->hsc[SC_TMP] = (ctx->rank == 0 && *flag) ? 1.0 : 0.0;
+    CU(ctx, cudaMemcpyAsync(ctx->dsc + SC_TMP, ctx->hsc + SC_TMP, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(allreduce_scalars(ctx, SC_TMP, 1));
+    TRY(fetch_scalars(ctx, SC_TMP, 1));
+    *flag = ctx->hsc[SC_TMP] > 0.5 ? 1 : 0;
+    return 0;
+}
+
 /* constraints this rank owns: all of them on one GPU; in a partitioned run those attached to its rows.  m-vector
  * kernels iterate t in [0, count) and touch entry k = gid ? gid[t] : t, so non-owned entries are never written. */
 struct Owned {
@@ -476,6 +493,10 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     lgpu_ctx *ctx = new lgpu_ctx();
     ctx->device = device;
     if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
+    if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
+    if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
+    if (const char *v = getenv("LORADS_STEP_STAGES")) ctx->step_stages = atoi(v);
+    if (const char *v = getenv("LORADS_SPMM_DOT")) ctx->spmm_dot = atoi(v) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1374,36 +1395,60 @@ static int mc_exchange(lgpu_ctx *ctx, const double *X)
                           ctx->send_rows, (int)c.ld, ctx->send_idx, X, ctx->sendbuf));
     }
     NC(ctx, g_nccl.GroupStart());
-    for (int q = 0; q < ctx->world; ++q) {
+    int bad = 0; /* an open group is always closed, also on the error path */
+    for (int q = 0; q < ctx->world && !bad; ++q) {
         if (q == ctx->rank) continue;
         if (ctx->send_cnt[q] > 0)
-            NC(ctx, g_nccl.Send(ctx->sendbuf + (size_t)ctx->send_off[q] * c.ld, (size_t)ctx->send_cnt[q] * c.ld, LG_NCCL_FLOAT64, q,
-                                (lg_ncclComm_t)ctx->comm, ctx->stream));
-        if (ctx->recv_cnt[q] > 0)
-            NC(ctx, g_nccl.Recv(ctx->halo + (size_t)ctx->recv_off[q] * c.ld, (size_t)ctx->recv_cnt[q] * c.ld, LG_NCCL_FLOAT64, q,
-                                (lg_ncclComm_t)ctx->comm, ctx->stream));
+            bad = g_nccl.Send(ctx->sendbuf + (size_t)ctx->send_off[q] * c.ld, (size_t)ctx->send_cnt[q] * c.ld, LG_NCCL_FLOAT64, q,
+                              (lg_ncclComm_t)ctx->comm, ctx->stream);
+        if (!bad && ctx->recv_cnt[q] > 0)
+            bad = g_nccl.Recv(ctx->halo + (size_t)ctx->recv_off[q] * c.ld, (size_t)ctx->recv_cnt[q] * c.ld, LG_NCCL_FLOAT64, q,
+                              (lg_ncclComm_t)ctx->comm, ctx->stream);
     }
-    NC(ctx, g_nccl.GroupEnd());
+    const int end_rc = g_nccl.GroupEnd();
+    NC(ctx, bad);
+    NC(ctx, end_rc);
     return 0;
 }
 
-/* T = C X ; X = this rank's rows (remote rows exchanged first in a partitioned run) */
-static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T)
+/* T = C X ; X = this rank's rows (remote rows exchanged first in a partitioned run).  dot_slot >= 0: the product's
+ * epilogue also leaves this rank's part of sum_i <X_i, T_i> in dsc[dot_slot] (not all-reduced: the caller's pack is) */
+static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T, int dot_slot = -1)
 {
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
     if (mc_exchange(ctx, X) != 0) return;
-    Prof pr(ctx, KC_MC_SPMM);
-    if (ctx->world > 1 && ctx->use_halo) {
-        const double *Xh = ctx->halo - (size_t)c.n_alloc * c.ld; /* halo row k is addressed as column n_alloc + k */
-        DISPATCH_G(G, k_mc_spmm<GG, 2, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, true>), LGPU_TPB, 0, ctx->stream>>>(
-                          c.n, c.f_ptr, c.f_col, c.mc_val, X, Xh, (int)c.n_alloc, (int)c.ld, T));
-        run_long_rows(ctx, c, c.ld, nullptr, c.mc_val, X, Xh, (int)c.n_alloc, 1.0, 0.0, nullptr, T);
-    } else {
-        const double *Xg = ctx->world > 1 ? ctx->gfull : X;
-        DISPATCH_G(G, k_mc_spmm<GG, 2, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, false>), LGPU_TPB, 0, ctx->stream>>>(
-                          c.n, c.f_ptr, c.f_col, c.mc_val, Xg, nullptr, 0, (int)c.ld, T));
-        run_long_rows(ctx, c, c.ld, nullptr, c.mc_val, Xg, nullptr, 0, 1.0, 0.0, nullptr, T);
+    const SlotSpec<1> sp = slot1(dot_slot >= 0 ? dot_slot : SC_TMP, 0);
+    const bool halo = ctx->world > 1 && ctx->use_halo;
+    const double *Xg = (ctx->world > 1 && !halo) ? ctx->gfull : X;
+    const double *Xh = halo ? ctx->halo - (size_t)c.n_alloc * c.ld : nullptr; /* halo row k is addressed as column n_alloc + k */
+    const int nsplit = halo ? (int)c.n_alloc : 0;
+    const int64_t self_off = (ctx->world > 1 && !halo) ? c.row_lo : 0;
+    {
+        Prof pr(ctx, KC_MC_SPMM);
+#define MC_SPMM(HALO, DOT)                                                                                                        \
+    DISPATCH_G(G, k_mc_spmm<GG, 2, HALO, DOT><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, HALO, DOT>), LGPU_TPB, 0,   \
+                                                ctx->stream>>>(c.n, c.f_ptr, c.f_col, c.mc_val, Xg, Xh, nsplit, (int)c.ld, T,      \
+                                                               self_off, ctx->partials, ctx->counter, ctx->dsc, sp))
+        if (halo) {
+            if (dot_slot >= 0) { MC_SPMM(true, true); } else { MC_SPMM(true, false); }
+        } else {
+            if (dot_slot >= 0) { MC_SPMM(false, true); } else { MC_SPMM(false, false); }
+        }
+#undef MC_SPMM
+        run_long_rows(ctx, c, c.ld, nullptr, c.mc_val, Xg, Xh, nsplit, 1.0, 0.0, nullptr, T);
+    }
+    if (dot_slot >= 0 && c.n_long > 0) {
+        /* hub rows were produced by the chunked kernels: add their <X_i, T_i> */
+        const int32_t *rows = c.long_rows;
+        const int64_t ld = c.ld;
+        const bool keep = ctx->defer_allreduce;
+        ctx->defer_allreduce = true;
+        launch_reduce<1>(ctx, c.n_long * ld, [=] __device__(int64_t q, double(&acc)[1]) {
+            const size_t o = (size_t)rows[q / ld] * ld + (size_t)(q % ld);
+            acc[0] = fma(X[o], T[o], acc[0]);
+        }, slot1(dot_slot, 1));
+        ctx->defer_allreduce = keep;
     }
 }
 static void mc_refresh_cr(lgpu_ctx *ctx)
@@ -1696,9 +1741,11 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
          * <C, R D^T> = <C R, D> (carried inner products), only p2 = <D, T> is left. */
         DevCone &c = ctx->cones[0];
         const int G = pick_group(c.ld);
-        mc_spmm_plain(ctx, ctx->U, ctx->CD);
+        /* p2 = <D, C D> rides in the product's epilogue when the direction pass already produced q1, q2, p1 */
+        mc_spmm_plain(ctx, ctx->U, ctx->CD, (ctx->epi_done && ctx->spmm_dot) ? SC_P2 : -1);
         ctx->defer_allreduce = true; /* local sums: p1, p2 and the five terms are all-reduced together below */
-        if (ctx->epi_done) {
+        if (ctx->epi_done && ctx->spmm_dot) {
+        } else if (ctx->epi_done) {
             const double *D = ctx->U, *T = ctx->CD;
             launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(D[i], T[i], acc[0]); },
                              slot1(SC_P2));
@@ -1834,7 +1881,52 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
     const int G = pick_group(c.ld);
     const bool gram = ctx->gram_enabled && ctx->h == 2;
     const int jn = ctx->head, jo = (ctx->head + 1) % ctx->h;
-    if (gram) {
+    /* bulk-copy pipeline (k_mc_step_bulk): tile rows / stages from ld so that a stage holds ~8 KB per stream and the ring
+     * fits the 227 KB of shared memory; very wide factors (small problems, L2-resident anyway) keep the register kernel */
+    int tr = 0, nstage = 0;
+    size_t bulk_smem = 0;
+    if (ctx->step_bulk) {
+        const int NG = LGPU_TPB / G;
+        tr = ctx->step_tile_rows > 0 ? ctx->step_tile_rows : (int)std::max<int64_t>(NG, std::min<int64_t>(64, 8192 / (c.ld * 8)));
+        tr = (tr + NG - 1) / NG * NG;
+        const size_t sb = step_bulk_stage_bytes(gram ? 7 : 5, tr, (int)c.ld);
+        nstage = (int)std::min<size_t>(LGPU_STEP_MAX_STAGES, (size_t)(226 * 1024) / sb);
+        if (ctx->step_stages > 0) nstage = std::min(nstage, ctx->step_stages);
+        bulk_smem = (size_t)nstage * sb + 2 * LGPU_STEP_MAX_STAGES * sizeof(uint64_t);
+        if (nstage < 2) tr = 0;
+    }
+    if (tr > 0) {
+        const int64_t ntiles = (c.n + tr - 1) / tr;
+        const int grid = (int)std::min<int64_t>(ntiles, ctx->num_sms);
+        const int threads = LGPU_TPB + 32 * nstage;
+        Prof pr(ctx, KC_MC_STEP);
+        if (gram) {
+            SlotSpec<10> sp;
+            for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
+            sp.accumulate = 0;
+            DISPATCH_G(G, {
+                auto kern = k_mc_step_bulk<GG, true>;
+                static bool attr_set = false;
+                if (!attr_set) { CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+                kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
+                                                               ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
+                                                               ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo], ctx->partials, ctx->counter,
+                                                               ctx->dsc, sp, SC_BETA0 + jn);
+            });
+        } else {
+            SlotSpec<3> sp;
+            sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
+            DISPATCH_G(G, {
+                auto kern = k_mc_step_bulk<GG, false>;
+                static bool attr_set = false;
+                if (!attr_set) { CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+                kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
+                                                               ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
+                                                               ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials, ctx->counter,
+                                                               ctx->dsc, sp, SC_BETA0 + jn);
+            });
+        }
+    } else if (gram) {
         SlotSpec<10> sp;
         for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
         sp.accumulate = 0;
@@ -2250,7 +2342,9 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
     const double *A = (phase == 1 ? ctx->R : ctx->U) + c.off;
     const double *B = ctx->V + c.off;
     dim3 grid(nchunks, nt * nt);
-    if (ctx->dense_dmma) {
+    if (nchunks == 0) {
+        /* a partition rank that owns no row of this cone: nothing to launch, k_gram_finish below writes zeros */
+    } else if (ctx->dense_dmma) {
         /* FP64 tensor pipe (DMMA), the default; lgpu_set_dense_tensor_path(0) selects the FMA kernel for A/B tests */
         Prof pr(ctx, KC_DENSE);
         const int64_t units = (int64_t)nchunks * nt * nt;
@@ -2460,7 +2554,17 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
         const double top = tridiag_extreme_eig(al, be, k + 1, +1);
         const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
         const double resid = bnorm * tridiag_last_component(al, be, k + 1, theta);
-        if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale || k + 1 >= kmax) break;
+        if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale) break;
+        if (k + 1 >= kmax) {
+            /* not converged: a Ritz value is only an UPPER bound of lambda_min, which would under-report the dual
+             * infeasibility; report the residual-corrected value (an eigenvalue lies within `resid` of theta) and say so */
+            if (kmax < n) {
+                fprintf(stderr, "lorads_b200: warning: Lanczos stopped after %d steps with Ritz residual %.3e (scale %.3e); "
+                                "dual infeasibility uses theta - residual\n", kmax, resid, scale);
+                theta -= resid;
+            }
+            break;
+        }
         double *qn = qptr(k + 1);
         const double inv = 1.0 / bnorm;
         launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * inv; });

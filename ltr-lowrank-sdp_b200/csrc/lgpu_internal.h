@@ -155,6 +155,7 @@ struct lgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
+    bool failed = false; /* sticky: set by every LGPU_FAIL, tested by CHECK_LAUNCH */
     int64_t launches = 0;
     int num_sms = 148;
 
@@ -196,6 +197,9 @@ struct lgpu_ctx {
     /* carried inner products of the two L-BFGS pairs and the current gradient (fused path, history length 2) */
     int step_variant = 1; /* min CTAs/SM of k_mc_step: 0 -> 2, 1 -> 3 (default; measured best: 80 registers, no spills), 2 -> 4, 3 -> 5 */
     bool gram_enabled = true;
+    bool spmm_dot = true;   /* <D, C D> in the sparse product's epilogue (LORADS_SPMM_DOT=0: separate pass, for A/B) */
+    int step_bulk = 1;      /* k_mc_step through the bulk-copy pipeline (LORADS_STEP_BULK=0: register-staged kernel) */
+    int step_tile_rows = 0, step_stages = 0; /* 0: chosen from ld (LORADS_STEP_TILE / LORADS_STEP_STAGES override) */
     bool gram_valid = false;
     bool gram_pair_ok[2] = {false, false};
     bool defer_allreduce = false; /* partitioned: keep local sums, a later call all-reduces the whole pack */

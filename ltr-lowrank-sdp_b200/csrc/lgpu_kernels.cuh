@@ -652,11 +652,16 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
  * warps, not per-thread tricks -- the same product with a software-pipelined (column, value) prefetch and 8 loads in
  * flight per lane needed 48-115 registers and ran 1.8-3.9x slower than this 32-register form at 8 CTAs per SM.
  * A group of G lanes owns a row; lane c holds 16-byte column word c; U entries are fetched per trip. */
-template <int G, int U, bool HALO>
+/* DOT: the product's epilogue also accumulates sum_i <X_i, T_i> = <C, X X^T> (the line search's p2 with X = D,
+ * lorads_alm.c:714-734).  Row i's own X words are re-read right after the walk that (on a MaxCut row, through the diagonal
+ * entry) just gathered them, i.e. from L1/L2: at most F extra bytes instead of the 2 F of a separate <D, T> pass.
+ * (Capturing them inside the walk instead cost 120 bytes of spills at the 32 registers that 8 CTAs per SM allow.) */
+template <int G, int U, bool HALO, bool DOT>
 __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
                                                          const int32_t *__restrict__ fcol, const double *__restrict__ fval,
                                                          const double *__restrict__ Xin, const double *__restrict__ Xhalo,
-                                                         int nsplit, int ld, double *__restrict__ T)
+                                                         int nsplit, int ld, double *__restrict__ T, int64_t self_off,
+                                                         double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec)
 {
     /* HALO: column ids < nsplit address this rank's own rows (Xin), the others the received halo rows; Xhalo is
      * passed pre-offset by -nsplit rows so both cases index with the column id itself */
@@ -665,6 +670,7 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
     const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int ld2 = ld >> 1;
+    double dot = 0.0;
     for (int64_t i = g0; i < n; i += groups) {
         const int e0 = fptr[i], e1 = fptr[i + 1];
         if (e1 - e0 > LGPU_LONG_ROW) continue; /* hub rows go to k_spmm_long_chunks */
@@ -690,9 +696,18 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
                 acc.x = fma(v, x.x, acc.x); acc.y = fma(v, x.y, acc.y);
             }
             reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
+            if (DOT) {
+                /* the row's own X words: on a MaxCut row they were just gathered for the diagonal entry (an L1/L2 hit) */
+                const double2 xd = reinterpret_cast<const double2 *>(Xin + (size_t)(i + self_off) * ld)[c];
+                dot = fma(xd.x, acc.x, dot); dot = fma(xd.y, acc.y, dot);
+            }
         }
     }
 #undef X_ROW
+    if (DOT) {
+        double red[1] = {dot};
+        grid_reduce_finish<1>(red, partials, counter, dsc, spec);
+    }
 }
 
 /* Rows of the symmetric CSR with more than LGPU_LONG_ROW entries (hub vertices, arrow-shaped patterns) are cut into
@@ -1079,6 +1094,242 @@ __global__ void __launch_bounds__(LGPU_TPB, MINB) k_mc_step(int64_t n, int ld, d
     const int ys_slot = spec.slot[1];
     grid_reduce_finish<NR>(red, partials, counter, dsc, spec,
                            [=] __device__(double *sc) { sc[beta_slot] = 1.0 / sc[ys_slot]; });
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * The same pass as k_mc_step, staged through shared memory by the bulk-copy engine (TMA, cp.async.bulk + mbarrier).
+ *
+ * Why: the register-staged kernel above needs 80 registers for its seven 16-byte loads and ten accumulators (3 CTAs per
+ * SM = 37 % of the warps) and every row starts with a dependent chain row -> constraint -> (q1, q2, cvs, lambda, b) ->
+ * coefficient that must resolve before the row's arithmetic can retire, so it ran at 0.82 of the copy bandwidth.  Here
+ * ONE persistent CTA per SM owns a ring of `nstage` shared-memory stages.  Producer warp p owns stage p: lane 0 arms
+ * the stage's mbarrier with the byte count and issues one 1-D bulk copy per input stream (a tile of `tr` consecutive
+ * rows of a row-major factor is one contiguous piece), while all its lanes walk the row -> constraint chain of the
+ * tile's rows (M1, the row coefficient, and for single-constraint rows the constraint id, a_k and b_k) into the
+ * stage.  Several tiles' chains are in flight at once because every producer warp runs its own.  The 8 consumer
+ * warps read the stage with conflict-free 16-byte shared loads, do exactly k_mc_step's arithmetic, store the five
+ * outputs straight to global memory and hand the stage back through a second mbarrier.  Bytes in flight per SM are set by
+ * nstage x tile size (>= 100 KB), not by registers.
+ * Waits are bounded: a protocol error traps (reported as a launch failure) instead of hanging the GPU.
+ * ------------------------------------------------------------------------------------------------*/
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0, spins = 0;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok) return;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#define LGPU_STEP_MAX_STAGES 4
+__host__ __device__ inline size_t step_bulk_stage_bytes(int nstream, int tr, int ld)
+{
+    /* nstream factor tiles + per-row {coef, a, b} doubles + {constraint id, count} ints, rounded to 128 bytes */
+    size_t b = (size_t)nstream * tr * ld * 8 + (size_t)tr * (3 * 8 + 2 * 4);
+    return (b + 127) / 128 * 128;
+}
+
+template <int G, bool GRAM>
+__global__ void __launch_bounds__(LGPU_TPB + 32 * LGPU_STEP_MAX_STAGES, 1)
+k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, double *__restrict__ Rm, const double *__restrict__ D,
+               double *__restrict__ CR, const double *__restrict__ T, double *__restrict__ Gd, double *__restrict__ sh,
+               double *__restrict__ yh, const int32_t *__restrict__ rcptr, const int32_t *__restrict__ rcgid,
+               const double *__restrict__ rca, const double *__restrict__ lam, const double *__restrict__ b,
+               double *__restrict__ cvs, const double *__restrict__ q1, const double *__restrict__ q2, double *__restrict__ M1,
+               const double *__restrict__ so, const double *__restrict__ yo, double *partials, unsigned int *counter, double *dsc,
+               SlotSpec<GRAM ? 10 : 3> spec, int beta_slot)
+{
+    constexpr int NSTREAM = GRAM ? 7 : 5;
+    constexpr int NR = GRAM ? 10 : 3;
+    constexpr int NG = LGPU_TPB / G;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int ld2 = ld >> 1;
+    const uint32_t tile_bytes = (uint32_t)tr * (uint32_t)ld * 8u;
+    const size_t stage_bytes = step_bulk_stage_bytes(NSTREAM, tr, ld);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)nstage * stage_bytes);
+    uint64_t *empty = full + LGPU_STEP_MAX_STAGES;
+    const int64_t ntiles = (n + tr - 1) / tr;
+    const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full[s], 1 + 32); /* lane 0's arrive.expect_tx + one arrive per producer lane */
+            mbar_init(&empty[s], LGPU_TPB / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= LGPU_TPB / 32) {
+        /* ---------------- producer warp p: stage p, tiles blockIdx.x + (p + j nstage) gridDim.x ---------------- */
+        const int p = warp - LGPU_TPB / 32;
+        if (p >= nstage) return;
+        unsigned char *base = smem + (size_t)p * stage_bytes;
+        double *scoef = reinterpret_cast<double *>(base + (size_t)NSTREAM * tile_bytes);
+        double *sra = scoef + tr, *srb = sra + tr;
+        int *srk = reinterpret_cast<int *>(srb + tr), *scnt = srk + tr;
+        const double t2 = tau * tau;
+        int it = 0;
+        for (int64_t s = p;; s += nstage, ++it) {
+            const int64_t tile = (int64_t)blockIdx.x + s * gridDim.x;
+            if (tile >= ntiles) break;
+            if (it > 0) mbar_wait(&empty[p], (uint32_t)((it - 1) & 1));
+            const int64_t row0 = tile * tr;
+            const int rows = (int)((n - row0 < tr) ? (n - row0) : tr);
+            if (lane32 == 0) {
+                const uint32_t bytes = (uint32_t)rows * (uint32_t)ld * 8u;
+                mbar_arrive_expect_tx(&full[p], NSTREAM * bytes);
+                const size_t off = (size_t)row0 * ld;
+                bulk_g2s(base + 0 * (size_t)tile_bytes, Rm + off, bytes, &full[p]);
+                bulk_g2s(base + 1 * (size_t)tile_bytes, D + off, bytes, &full[p]);
+                bulk_g2s(base + 2 * (size_t)tile_bytes, CR + off, bytes, &full[p]);
+                bulk_g2s(base + 3 * (size_t)tile_bytes, T + off, bytes, &full[p]);
+                bulk_g2s(base + 4 * (size_t)tile_bytes, Gd + off, bytes, &full[p]);
+                if (GRAM) {
+                    bulk_g2s(base + 5 * (size_t)tile_bytes, so + off, bytes, &full[p]);
+                    bulk_g2s(base + 6 * (size_t)tile_bytes, yo + off, bytes, &full[p]);
+                }
+            }
+            for (int rr = lane32; rr < rows; rr += 32) {
+                const int64_t i = row0 + rr;
+                const int k0 = rcptr[i], k1 = rcptr[i + 1];
+                double coef = 0.0;
+                for (int t = k0; t < k1; ++t) {
+                    const int k = rcgid[t];
+                    const double cv = fma(t2, q2[k], fma(tau, q1[k], cvs[k]));
+                    const double m1 = -lam[k] - rho * b[k] + rho * cv;
+                    M1[k] = m1;
+                    coef = fma(m1, rca[t], coef);
+                }
+                scoef[rr] = coef;
+                scnt[rr] = k1 - k0;
+                if (k1 - k0 == 1) {
+                    const int k = rcgid[k0];
+                    srk[rr] = k;
+                    sra[rr] = rca[k0];
+                    srb[rr] = b[k];
+                } else {
+                    srk[rr] = k0;
+                }
+            }
+            mbar_arrive(&full[p]);
+        }
+        return;
+    }
+
+    /* ---------------- consumers: 8 warps, a group of G lanes per row ---------------- */
+    const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+    double red[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) red[k] = 0.0;
+    int st = 0, it = 0;
+    for (int64_t s = 0;; ++s) {
+        const int64_t tile = (int64_t)blockIdx.x + s * gridDim.x;
+        if (tile >= ntiles) break;
+        mbar_wait(&full[st], (uint32_t)(it & 1));
+        const unsigned char *base = smem + (size_t)st * stage_bytes;
+        const double2 *sR = reinterpret_cast<const double2 *>(base);
+        const double2 *sD = reinterpret_cast<const double2 *>(base + 1 * (size_t)tile_bytes);
+        const double2 *sC = reinterpret_cast<const double2 *>(base + 2 * (size_t)tile_bytes);
+        const double2 *sT = reinterpret_cast<const double2 *>(base + 3 * (size_t)tile_bytes);
+        const double2 *sG = reinterpret_cast<const double2 *>(base + 4 * (size_t)tile_bytes);
+        const double2 *sSo = reinterpret_cast<const double2 *>(base + 5 * (size_t)tile_bytes);
+        const double2 *sYo = reinterpret_cast<const double2 *>(base + 6 * (size_t)tile_bytes);
+        const double *scoef = reinterpret_cast<const double *>(base + (size_t)NSTREAM * tile_bytes);
+        const double *sra = scoef + tr, *srb = sra + tr;
+        const int *srk = reinterpret_cast<const int *>(srb + tr), *scnt = srk + tr;
+        const int64_t row0 = tile * tr;
+        const int rows = (int)((n - row0 < tr) ? (n - row0) : tr);
+        for (int rb = 0; rb < tr; rb += NG) { /* every group runs the same trip count: the shuffles stay convergent */
+            const int rr = rb + grp;
+            const bool live = rr < rows;
+            double rsq = 0.0;
+            if (live) {
+                const double coef = scoef[rr];
+                for (int c = lane; c < ld2; c += G) {
+                    const int ws = rr * ld2 + c;
+                    const size_t w = (size_t)(row0 + rr) * ld2 + c;
+                    double2 r = sR[ws];
+                    const double2 d = sD[ws];
+                    double2 cr = sC[ws];
+                    const double2 t = sT[ws];
+                    const double2 go = sG[ws];
+                    r.x = fma(tau, d.x, r.x); r.y = fma(tau, d.y, r.y);
+                    cr.x = fma(tau, t.x, cr.x); cr.y = fma(tau, t.y, cr.y);
+                    double2 gn;
+                    gn.x = 2.0 * fma(coef, r.x, cr.x);
+                    gn.y = 2.0 * fma(coef, r.y, cr.y);
+                    const double2 sv = make_double2(tau * d.x, tau * d.y);
+                    const double2 yv = make_double2(-go.x + gn.x, -go.y + gn.y);
+                    reinterpret_cast<double2 *>(Rm)[w] = r;
+                    reinterpret_cast<double2 *>(CR)[w] = cr;
+                    reinterpret_cast<double2 *>(Gd)[w] = gn;
+                    reinterpret_cast<double2 *>(sh)[w] = sv;
+                    reinterpret_cast<double2 *>(yh)[w] = yv;
+                    red[0] = fma(gn.x, gn.x, red[0]); red[0] = fma(gn.y, gn.y, red[0]);
+                    red[1] = fma(yv.x, sv.x, red[1]); red[1] = fma(yv.y, sv.y, red[1]);
+                    if (GRAM) {
+                        const double2 os = sSo[ws];
+                        const double2 oy = sYo[ws];
+                        red[3] = fma(gn.x, sv.x, red[3]); red[3] = fma(gn.y, sv.y, red[3]);
+                        red[4] = fma(gn.x, yv.x, red[4]); red[4] = fma(gn.y, yv.y, red[4]);
+                        red[5] = fma(gn.x, os.x, red[5]); red[5] = fma(gn.y, os.y, red[5]);
+                        red[6] = fma(gn.x, oy.x, red[6]); red[6] = fma(gn.y, oy.y, red[6]);
+                        red[7] = fma(os.x, yv.x, red[7]); red[7] = fma(os.y, yv.y, red[7]);
+                        red[8] = fma(oy.x, yv.x, red[8]); red[8] = fma(oy.y, yv.y, red[8]);
+                        red[9] = fma(yv.x, yv.x, red[9]); red[9] = fma(yv.y, yv.y, red[9]);
+                    }
+                    rsq = fma(r.x, r.x, rsq); rsq = fma(r.y, r.y, rsq);
+                }
+            }
+            rsq = group_sum<G>(rsq);
+            if (live && lane == 0) {
+                const int cnt = scnt[rr];
+                if (cnt == 1) {
+                    const double cv = sra[rr] * rsq;
+                    cvs[srk[rr]] = cv;
+                    const double df = srb[rr] - cv;
+                    red[2] = fma(df, df, red[2]);
+                } else {
+                    const int k0 = srk[rr];
+                    for (int t = k0; t < k0 + cnt; ++t) {
+                        const int k = rcgid[t];
+                        const double cv = rca[t] * rsq;
+                        cvs[k] = cv;
+                        const double df = b[k] - cv;
+                        red[2] = fma(df, df, red[2]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane32 == 0) mbar_arrive(&empty[st]);
+        if (++st == nstage) { st = 0; ++it; }
+    }
+    const int ys_slot = spec.slot[1];
+    grid_reduce_finish<NR>(red, partials, counter, dsc, spec, [=] __device__(double *sc) { sc[beta_slot] = 1.0 / sc[ys_slot]; });
 }
 
 /* Grad = 2 (CR + Diag(sum_k M1_k a_k) R) and sum Grad^2, with CR = C R already formed    lorads_alm.c:32-87 */

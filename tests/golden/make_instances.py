@@ -65,6 +65,29 @@ def gen_maxcut_torus(path, rows, cols, seed):
     write_sdpa(path, n, [n], np.ones(n), maxcut_entries(n, edges, w))
 
 
+def gen_g1(path, mtx="/root/reference/hallar/py/graphs/G1.mtx"):
+    """BASELINE configs[0]: G-set G1 (n = m = 800, 19176 unit-weight edges) from the MatrixMarket pattern file the
+    reference ships, in the gen_MaxCut.jl convention (reference LoRADS: objective -24166.3)."""
+    edges = []
+    with open(mtx) as f:
+        for line in f:
+            if line.startswith("%"):
+                continue
+            t = line.split()
+            if len(t) == 3 and not edges and int(t[0]) == int(t[1]):   # size line: rows cols nnz
+                n = int(t[0])
+                continue
+            i, j = int(t[0]) - 1, int(t[1]) - 1
+            if i != j:
+                edges.append((min(i, j), max(i, j)))
+    edges = sorted(set(edges))
+    # gen_MaxCut.jl / bundled G11.dat-s sign: the FILE holds F0 = +L/2 (the reader negates it, lorads_file_io.c:317-319),
+    # i.e. the opposite sign of maxcut_entries() above, whose +-1-weight fixtures do not depend on it
+    ent = [(c, k, i, j, (-v if c == 0 else v)) for (c, k, i, j, v) in maxcut_entries(n, edges, [1.0] * len(edges))]
+    write_sdpa(path, n, [n], np.ones(n), ent)
+    return n, len(edges)
+
+
 def gen_general_sparse(path, n, m, seed):
     """Sparse aggregate (< 10% of the triangle), every constraint has several off-diagonal entries."""
     rng = np.random.default_rng(seed)
@@ -197,6 +220,8 @@ def main():
     gen_dense_constraint(os.path.join(OUT, "dense_constraint_n24.dat-s"), 24, 12, 9)
     gen_multiblock(os.path.join(OUT, "multiblock_sdp.dat-s"), [25, 30, 22, 28], 0, 40, 13, lp=False)
     gen_multiblock(os.path.join(OUT, "multiblock_lp.dat-s"), [25, 30, 22, 28], 12, 40, 17, lp=True)
+    if os.path.exists("/root/reference/hallar/py/graphs/G1.mtx"):
+        print("G1:", gen_g1(os.path.join(OUT, "G1.dat-s")))
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -430,6 +430,60 @@ def test_fused_path_rank_extremes(lb, r):
     assert rel(out[True][3], out[False][3]) < 1e-4
 
 
+def _diag_problem_irregular_rows(lb, n, seed):
+    """diag-only cone whose row -> constraint map is NOT the identity: rows 0..4 carry three constraints each, the last
+    ten rows none, with unequal coefficients -- the general branch of the fused kernels' row/constraint walk"""
+    ei, ej, w = lb.random_graph(n, 4, seed)
+    rng = np.random.default_rng(seed)
+    w = rng.choice([-1.0, 1.0], size=len(ei))
+    base = lb.maxcut_problem(n, ei, ej, w)
+    nobj = int(base.mat_beg[0][1])
+    rows = np.concatenate([np.arange(n - 10), np.repeat(np.arange(5), 2)]).astype(np.int64)
+    coef = rng.uniform(0.5, 2.0, size=n)
+    beg = np.concatenate([[0], nobj + np.arange(n + 1, dtype=np.int64)])
+    idx = np.concatenate([base.mat_idx[0][:nobj], lb.pack_idx(n, rows, rows)])
+    val = np.concatenate([base.mat_elem[0][:nobj], coef])
+    return lb.SdpaProblem(n, [n], rng.uniform(0.5, 1.5, size=n), [beg], [idx], [val])
+
+
+@pytest.mark.parametrize("n,r", [(1500, 32), (4099, 12), (777, 70)])
+def test_step_and_product_kernel_variants_agree(lb, monkeypatch, n, r):
+    """k_mc_step_bulk (bulk-copy pipeline: several tile sizes / ring depths, ragged last tile, rows with 0 / 1 / 3
+    constraints) and the <D, C D> epilogue of the sparse product against the register-staged step kernel with a separate
+    dot pass: same trajectory to rounding over 10 ALM inner iterations."""
+    p = _diag_problem_irregular_rows(lb, n, r)
+    rng = np.random.default_rng(n)
+    R0 = rng.random((n, r)) - rng.random((n, r))
+    rho = 1.0 / np.sqrt(n)
+    settings = [{"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0"}, {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"},
+                {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "16", "LORADS_STEP_STAGES": "4"},
+                {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "8", "LORADS_STEP_STAGES": "2"},
+                {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "40", "LORADS_STEP_STAGES": "3"}]
+    outs = []
+    for env in settings:
+        for k in ("LORADS_STEP_BULK", "LORADS_SPMM_DOT", "LORADS_STEP_TILE", "LORADS_STEP_STAGES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = lb.Context(0).load(p)
+        ctx.alloc_vars([r], 2)
+        assert ctx.uses_fused_path()
+        ctx.set_factor(lb.R, 0, R0)
+        ctx.init_constr_val(lb.PAIR_RR)
+        ctx.alm_cal_grad(rho)
+        hist = []
+        for it in range(10):
+            ctx.lbfgs_direction(it)
+            terms = ctx.alm_linesearch_terms(rho)
+            _, tau = _line_search(lb, rho, terms)
+            hist.append((tau,) + tuple(terms) + ctx.alm_inner_update(rho, tau))
+        outs.append((np.array(hist), ctx.get_factor(lb.R, 0), ctx.get_vec(lb.VEC_CONSTR_SUM), ctx.get_factor(lb.GRAD, 0)))
+        ctx.close()
+    for o in outs[1:]:
+        assert np.all(np.abs(o[0] - outs[0][0]) <= 1e-9 * np.abs(outs[0][0]) + 1e-300)
+        assert rel(o[1], outs[0][1]) < 1e-11 and rel(o[2], outs[0][2]) < 1e-11 and rel(o[3], outs[0][3]) < 1e-9
+
+
 def test_fused_path_tracks_general_path_at_c3_scale(lb):
     """A/B at the G81-like size (n = 20000, rank 20): 40 ALM inner iterations + dual update + 1 ADMM sweep on the
     fused MaxCut-type path and on the general path from the same start; trajectories must agree far inside the
