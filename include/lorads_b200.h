@@ -212,6 +212,9 @@ int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int rank, int wor
  * *flag is rank 0's value on every rank (rank 0 is authoritative), so all ranks leave a loop in the same iteration
  * and nobody is left waiting inside the next collective.  One GPU: *flag is returned unchanged. */
 int lgpu_agree_flag(lgpu_ctx *ctx, int *flag);
+/* 1 when the ranks exchange halo rows and scalar packs through peer-mapped memory (NVLink stores from our own kernels,
+ * CUDA IPC), 0 when they use ncclSend/ncclRecv/ncclAllReduce (LORADS_PEER=0, no peer access, or two ranks on one GPU) */
+int lgpu_uses_peer_exchange(const lgpu_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ typedef struct {
     const char *rankScheduleFile;
     double nearStallFactor;
     int disableOracle;
+    int jsonFinalMetrics;
     /* B200 additions */
     int device;
     int quiet;

@@ -264,6 +264,15 @@ static bool nccl_load(std::string &err)
 static int allreduce_scalars(lgpu_ctx *ctx, int first, int count)
 {
     if (ctx->world <= 1) return 0;
+    if (ctx->peer && count <= LGPU_PEER_RED) {
+        PeerRed pr;
+        pr.world = ctx->world;
+        pr.rank = ctx->rank;
+        for (int q = 0; q < ctx->world; ++q) pr.blk[q] = ctx->peer_blk[q];
+        Prof pf(ctx, KC_SCALAR);
+        k_peer_allreduce<<<1, LGPU_MAX_WORLD * LGPU_PEER_RED, 0, ctx->stream>>>(ctx->dsc, first, count, pr, ++ctx->aseq);
+        return 0;
+    }
     NC(ctx, g_nccl.AllReduce(ctx->dsc + first, ctx->dsc + first, (size_t)count, LG_NCCL_FLOAT64, LG_NCCL_SUM,
                              (lg_ncclComm_t)ctx->comm, ctx->stream));
     return 0;
@@ -276,6 +285,124 @@ static int allreduce_spec(lgpu_ctx *ctx, const SlotSpec<K> &sp)
     for (int k = 1; k < K; ++k) { lo = std::min(lo, sp.slot[k]); hi = std::max(hi, sp.slot[k]); }
     if (hi - lo + 1 == K) return allreduce_scalars(ctx, lo, K);
     for (int k = 0; k < K; ++k) TRY(allreduce_scalars(ctx, sp.slot[k], 1));
+    return 0;
+}
+
+/* ---- peer-memory mapping (CUDA IPC) ------------------------------------------------------------------------
+ * A record per rank (IPC handle of an allocation + the PCI bus id of its GPU) is all-gathered through the NCCL
+ * communicator; every rank opens the others' handles.  Peer mode needs: one GPU per rank (distinct bus ids), peer
+ * access between all pairs, and every handle opening -- the decision is all-reduced so that either every rank uses the
+ * peer path or none does.  LORADS_PEER=0 keeps the NCCL path. */
+struct PeerRecord {
+    cudaIpcMemHandle_t handle; /* 64 bytes */
+    char bus[32];
+    int ok;
+    int pad;
+    long long rows; /* halo rows of the exporting rank */
+    long long pad2[2];
+};
+static int peer_allgather_records(lgpu_ctx *ctx, const PeerRecord &mine, std::vector<PeerRecord> &all)
+{
+    const int P = ctx->world;
+    all.assign(P, PeerRecord());
+    PeerRecord *d = nullptr;
+    CU(ctx, cudaMalloc((void **)&d, sizeof(PeerRecord) * P));
+    CU(ctx, cudaMemcpyAsync(d + ctx->rank, &mine, sizeof(PeerRecord), cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, g_nccl.AllGather(d + ctx->rank, d, sizeof(PeerRecord), /* ncclInt8 */ 0, (lg_ncclComm_t)ctx->comm, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(all.data(), d, sizeof(PeerRecord) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return 0;
+}
+/* every rank passes its local verdict; returns the conjunction (NCCL sum of the refusals) */
+static int peer_all_agree(lgpu_ctx *ctx, bool mine, bool *all)
+{
+    ctx->hsc[SC_TMP] = mine ? 0.0 : 1.0;
+    CU(ctx, cudaMemcpyAsync(ctx->dsc + SC_TMP, ctx->hsc + SC_TMP, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NC(ctx, g_nccl.AllReduce(ctx->dsc + SC_TMP, ctx->dsc + SC_TMP, 1, LG_NCCL_FLOAT64, LG_NCCL_SUM, (lg_ncclComm_t)ctx->comm,
+                             ctx->stream));
+    TRY(fetch_scalars(ctx, SC_TMP, 1));
+    *all = ctx->hsc[SC_TMP] < 0.5;
+    return 0;
+}
+static int peer_setup(lgpu_ctx *ctx)
+{
+    ctx->peer = false;
+    const int P = ctx->world;
+    bool want = P > 1 && P <= LGPU_MAX_WORLD;
+    if (const char *v = getenv("LORADS_PEER")) want = want && atoi(v) != 0;
+    PeerRecord mine;
+    memset(&mine, 0, sizeof(mine));
+    if (want) {
+        if (cudaMalloc((void **)&ctx->blk, sizeof(PeerBlock)) != cudaSuccess) { cudaGetLastError(); want = false; ctx->blk = nullptr; }
+        else {
+            cudaMemset(ctx->blk, 0, sizeof(PeerBlock));
+            if (cudaIpcGetMemHandle(&mine.handle, ctx->blk) != cudaSuccess) { cudaGetLastError(); want = false; }
+        }
+        if (cudaDeviceGetPCIBusId(mine.bus, sizeof(mine.bus), ctx->device) != cudaSuccess) { cudaGetLastError(); want = false; }
+    }
+    mine.ok = want ? 1 : 0;
+    std::vector<PeerRecord> all;
+    TRY(peer_allgather_records(ctx, mine, all));
+    bool ok = want;
+    for (int q = 0; q < P && ok; ++q) {
+        if (!all[q].ok) ok = false;
+        for (int s = 0; s < q && ok; ++s)
+            if (strncmp(all[q].bus, all[s].bus, sizeof(mine.bus)) == 0) ok = false; /* two ranks on one GPU: spinning kernels may not co-run */
+    }
+    for (int q = 0; q < P && ok; ++q) {
+        if (q == ctx->rank) { ctx->peer_blk[q] = ctx->blk; continue; }
+        int dev = -1, can = 0;
+        if (cudaDeviceGetByPCIBusId(&dev, all[q].bus) != cudaSuccess || cudaDeviceCanAccessPeer(&can, ctx->device, dev) != cudaSuccess || !can) {
+            cudaGetLastError();
+            ok = false;
+            break;
+        }
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        ctx->peer_blk[q] = (PeerBlock *)ptr;
+    }
+    bool every = false;
+    TRY(peer_all_agree(ctx, ok, &every));
+    ctx->peer = every;
+    if (every && ctx->put_counter == nullptr) {
+        CU(ctx, cudaMalloc((void **)&ctx->put_counter, sizeof(unsigned int)));
+        CU(ctx, cudaMemset(ctx->put_counter, 0, sizeof(unsigned int)));
+    }
+    if (getenv("LORADS_PEER_VERBOSE") && ctx->rank == 0)
+        fprintf(stderr, "lorads_b200: peer-memory exchange %s (%d ranks)\n", every ? "enabled" : "unavailable, using NCCL", P);
+    return 0;
+}
+static int peer_unmap_halo(lgpu_ctx *ctx, bool barrier)
+{
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int q = 0; q < ctx->world; ++q) {
+        if (q != ctx->rank && ctx->peer_halo[q]) cudaIpcCloseMemHandle(ctx->peer_halo[q]);
+        ctx->peer_halo[q] = nullptr;
+    }
+    if (!barrier) return 0;
+    bool all = false;
+    return peer_all_agree(ctx, true, &all); /* barrier: nobody frees a buffer a peer still maps */
+}
+/* (re)map the halo allocations of all ranks: called by every rank whenever the halo is (re)allocated */
+static int peer_map_halo(lgpu_ctx *ctx)
+{
+    const int P = ctx->world;
+    PeerRecord mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = cudaIpcGetMemHandle(&mine.handle, ctx->halo) == cudaSuccess ? 1 : 0;
+    if (!mine.ok) cudaGetLastError();
+    mine.rows = ctx->halo_rows;
+    std::vector<PeerRecord> all;
+    TRY(peer_allgather_records(ctx, mine, all));
+    for (int q = 0; q < P; ++q) {
+        if (!all[q].ok) LGPU_FAIL(ctx, "rank %d could not export its halo buffer (CUDA IPC)", q);
+        ctx->peer_halo_rows[q] = all[q].rows;
+        if (q == ctx->rank) { ctx->peer_halo[q] = ctx->halo; continue; }
+        void *ptr = nullptr;
+        CU(ctx, cudaIpcOpenMemHandle(&ptr, all[q].handle, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_halo[q] = (double *)ptr;
+    }
     return 0;
 }
 
@@ -311,9 +438,10 @@ extern "C" int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int ra
     ctx->comm = comm;
     ctx->rank = rank;
     ctx->world = world;
-    return 0;
+    return peer_setup(ctx);
 }
 
+extern "C" int lgpu_uses_peer_exchange(const lgpu_ctx *ctx) { return (ctx && ctx->peer) ? 1 : 0; }
 extern "C" int lgpu_agree_flag(lgpu_ctx *ctx, int *flag)
 {
     if (!ctx || !flag) return 1;
@@ -496,7 +624,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
     if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
     if (const char *v = getenv("LORADS_STEP_STAGES")) ctx->step_stages = atoi(v);
-    if (const char *v = getenv("LORADS_SPMM_DOT")) ctx->spmm_dot = atoi(v) != 0;
+    if (const char *v = getenv("LORADS_SPMM_DOT")) ctx->spmm_dot = atoi(v);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -565,7 +693,7 @@ extern "C" int lgpu_profile_num_classes(void) { return KC_COUNT; }
 extern "C" const char *lgpu_profile_class_name(int cls)
 {
     static const char *names[KC_COUNT] = {"k_uvt", "k_gather", "k_wsum", "k_spmm", "k_vec", "k_reduce", "k_scalar",
-                                          "k_layout", "k_mc_spmm", "k_mc_step", "k_mc_dir", "k_dense_dmma"};
+                                          "k_layout", "k_mc_spmm", "k_mc_step", "k_mc_dir", "k_dense_dmma", "k_exchange"};
     return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
 }
 
@@ -581,8 +709,12 @@ static void free_cone(DevCone &c)
     dev_free(c.mc_val); dev_free(c.rc_ptr); dev_free(c.rc_gid); dev_free(c.rc_a);
     dev_free(c.uvt); dev_free(c.S); dev_free(c.cv); dev_free(c.wtmp);
 }
-static void free_vars(lgpu_ctx *ctx)
+static int peer_unmap_halo(lgpu_ctx *ctx, bool barrier);
+/* collective = every rank is in the same call (alloc / aug_rank / set_problem): the peers' mappings of this rank's halo
+ * are closed, with a barrier, before the buffer is freed */
+static void free_vars(lgpu_ctx *ctx, bool collective = true)
 {
+    if (ctx->peer && ctx->halo != nullptr) peer_unmap_halo(ctx, collective);
     dev_free(ctx->R); dev_free(ctx->U); dev_free(ctx->V); dev_free(ctx->G); dev_free(ctx->M2); dev_free(ctx->bLin);
     dev_free(ctx->cg_r); dev_free(ctx->cg_p); dev_free(ctx->cg_Q); dev_free(ctx->stage);
     dev_free(ctx->CR); dev_free(ctx->CD); dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
@@ -601,7 +733,10 @@ extern "C" void lgpu_destroy(lgpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &c : ctx->cones) free_cone(c);
-    free_vars(ctx);
+    free_vars(ctx, false);
+    for (int q = 0; q < ctx->world; ++q)
+        if (ctx->peer && q != ctx->rank && ctx->peer_blk[q]) cudaIpcCloseMemHandle(ctx->peer_blk[q]);
+    dev_free(ctx->blk); dev_free(ctx->put_counter);
     dev_free(ctx->b); dev_free(ctx->lam); dev_free(ctx->cvs); dev_free(ctx->q1); dev_free(ctx->q2); dev_free(ctx->M1);
     dev_free(ctx->mtmp);
     dev_free(ctx->lp.obj); dev_free(ctx->lp.r_ptr); dev_free(ctx->lp.r_col); dev_free(ctx->lp.r_val);
@@ -786,7 +921,7 @@ extern "C" int lgpu_cone_layout_get(const lgpu_layout *layout, const char *name,
     LQ_ARRAY(t_val, 8) LQ_ARRAY(f_ptr, 4) LQ_ARRAY(f_col, 4) LQ_ARRAY(f_slot, 4) LQ_ARRAY(d_row, 4) LQ_ARRAY(d_val, 8)
     LQ_ARRAY(mc_val, 8) LQ_ARRAY(rc_ptr, 4) LQ_ARRAY(rc_gid, 4) LQ_ARRAY(rc_a, 8) LQ_ARRAY(lf_ptr, 4) LQ_ARRAY(lf_col, 4)
     LQ_ARRAY(lmc_val, 8) LQ_ARRAY(lrc_ptr, 4) LQ_ARRAY(lrc_gid, 4) LQ_ARRAY(lrc_a, 8) LQ_ARRAY(send_idx, 4) LQ_ARRAY(halo_gid, 4)
-    LQ_ARRAY(send_off, -8) LQ_ARRAY(send_cnt, -8) LQ_ARRAY(recv_off, -8) LQ_ARRAY(recv_cnt, -8)
+    LQ_ARRAY(send_off, -8) LQ_ARRAY(send_cnt, -8) LQ_ARRAY(recv_off, -8) LQ_ARRAY(recv_cnt, -8) LQ_ARRAY(dst_off, -8)
 #undef LQ_ARRAY
     if (nm == "scalars") {
         sc = {(double)L.mA, (double)L.nnzP, (double)L.nnzA, (double)L.nnzC, (double)L.nnzF, (double)L.max_con_len,
@@ -815,7 +950,7 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     ConeLayout L;
     {
         std::string err;
-        if (build_cone_layout(n, m, beg, idx_in, val_in, ctx->world, ctx->rank, ctx->ncones == 1 && ctx->lp.n == 0, L, err))
+        if (build_cone_layout(n, m, beg, idx_in, val_in, ctx->world, ctx->rank, ctx->ncones == 1 && ctx->lp.n == 0, L, err, ctx->peer))
             LGPU_FAIL(ctx, "%s", err.c_str());
     }
     free_cone(c);
@@ -845,6 +980,7 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         ctx->halo_rows = L.halo_rows;
         ctx->send_rows = L.send_rows;
         ctx->use_halo = L.use_halo;
+        ctx->dst_off = L.dst_off;
         if (L.use_halo) {
             dev_free(ctx->send_idx);
             TRY(dev_upload(ctx, &ctx->send_idx, L.send_idx));
@@ -1095,7 +1231,13 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     }
     if (ctx->world > 1) {
         dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
-        if (ctx->use_halo) {
+        if (ctx->use_halo && ctx->peer) {
+            /* two halo buffers, used alternately: a fast peer may already PUT the next exchange's rows while this rank's
+             * product still reads the current ones (DESIGN.md "Multi-GPU") */
+            const size_t ld = (size_t)ctx->cones[0].ld;
+            TRY(dev_alloc(ctx, &ctx->halo, 2 * (size_t)std::max<int64_t>(ctx->halo_rows, 1) * ld));
+            TRY(peer_map_halo(ctx));
+        } else if (ctx->use_halo) {
             const size_t ld = (size_t)ctx->cones[0].ld;
             TRY(dev_alloc(ctx, &ctx->halo, (size_t)ctx->halo_rows * ld));
             TRY(dev_alloc(ctx, &ctx->sendbuf, (size_t)ctx->send_rows * ld));
@@ -1389,6 +1531,35 @@ static int mc_exchange(lgpu_ctx *ctx, const double *X)
     }
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
+    if (ctx->peer) {
+        /* PUT the rows every peer's CSR references straight into its halo buffer, then wait for the sources of mine */
+        const unsigned long long seq = ++ctx->xseq;
+        const size_t buf = (size_t)(seq & 1ull) * (size_t)std::max<int64_t>(ctx->halo_rows, 1) * (size_t)c.ld;
+        PeerPut pp;
+        pp.world = ctx->world;
+        pp.rank = ctx->rank;
+        for (int q = 0; q < ctx->world; ++q) {
+            pp.send_off[q] = ctx->send_off[q];
+            /* rank q's two buffers have q's halo size: its second buffer starts at peer_halo_rows[q] * ld */
+            pp.dst[q] = q == ctx->rank ? nullptr
+                                       : ctx->peer_halo[q] + (size_t)(seq & 1ull) * (size_t)std::max<int64_t>(ctx->peer_halo_rows[q], 1) * (size_t)c.ld +
+                                             (size_t)ctx->dst_off[q] * (size_t)c.ld;
+            pp.flag[q] = &ctx->peer_blk[q]->xflag[ctx->rank];
+        }
+        pp.send_off[ctx->world] = ctx->send_rows;
+        {
+            Prof pr(ctx, KC_EXCH);
+            DISPATCH_G(G, k_put_rows<GG><<<grid_for(ctx, std::max<int64_t>(ctx->send_rows, 1) * GG, (const void *)k_put_rows<GG>), LGPU_TPB, 0,
+                                          ctx->stream>>>(ctx->send_rows, (int)c.ld, ctx->send_idx, X, pp, seq, ctx->put_counter));
+        }
+        {
+            Prof pr(ctx, KC_EXCH);
+            k_wait_sources<<<1, 32, 0, ctx->stream>>>(ctx->blk->xflag, ctx->world, ctx->rank, seq);
+        }
+        ctx->halo_cur = ctx->halo + buf;
+        return 0;
+    }
+    ctx->halo_cur = ctx->halo;
     if (ctx->send_rows > 0) {
         Prof pr(ctx, KC_LAYOUT);
         DISPATCH_G(G, k_pack_rows<GG><<<grid_for(ctx, ctx->send_rows * GG, (const void *)k_pack_rows<GG>), LGPU_TPB, 0, ctx->stream>>>(
@@ -1421,19 +1592,33 @@ static void mc_spmm_plain(lgpu_ctx *ctx, const double *X, double *T, int dot_slo
     const SlotSpec<1> sp = slot1(dot_slot >= 0 ? dot_slot : SC_TMP, 0);
     const bool halo = ctx->world > 1 && ctx->use_halo;
     const double *Xg = (ctx->world > 1 && !halo) ? ctx->gfull : X;
-    const double *Xh = halo ? ctx->halo - (size_t)c.n_alloc * c.ld : nullptr; /* halo row k is addressed as column n_alloc + k */
+    const double *Xh = halo ? ctx->halo_cur - (size_t)c.n_alloc * c.ld : nullptr; /* halo row k is addressed as column n_alloc + k */
     const int nsplit = halo ? (int)c.n_alloc : 0;
     const int64_t self_off = (ctx->world > 1 && !halo) ? c.row_lo : 0;
     {
         Prof pr(ctx, KC_MC_SPMM);
-#define MC_SPMM(HALO, DOT)                                                                                                        \
-    DISPATCH_G(G, k_mc_spmm<GG, 2, HALO, DOT><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, HALO, DOT>), LGPU_TPB, 0,   \
-                                                ctx->stream>>>(c.n, c.f_ptr, c.f_col, c.mc_val, Xg, Xh, nsplit, (int)c.ld, T,      \
-                                                               self_off, ctx->partials, ctx->counter, ctx->dsc, sp))
+#define MC_SPMM(HALO, DOT, MINB)                                                                                                  \
+    DISPATCH_G(G, k_mc_spmm<GG, 2, HALO, DOT, MINB><<<grid_for(ctx, c.n * GG, (const void *)k_mc_spmm<GG, 2, HALO, DOT, MINB>),    \
+                                                      LGPU_TPB, 0, ctx->stream>>>(c.n, c.f_ptr, c.f_col, c.mc_val, Xg, Xh, nsplit, \
+                                                                                  (int)c.ld, T, self_off, ctx->partials,         \
+                                                                                  ctx->counter, ctx->dsc, sp))
+        const int mode = dot_slot >= 0 ? ctx->spmm_dot : 0;
         if (halo) {
-            if (dot_slot >= 0) { MC_SPMM(true, true); } else { MC_SPMM(true, false); }
+            switch (mode) {
+            case 0: MC_SPMM(true, 0, 8); break;
+            case 1: MC_SPMM(true, 1, 8); break;
+            case 2: MC_SPMM(true, 2, 7); break;
+            case 4: MC_SPMM(true, 1, 7); break;
+            default: MC_SPMM(true, 2, 6); break; /* measured best at C5: 13.67 ms / iteration vs 13.95 with the separate pass */
+            }
         } else {
-            if (dot_slot >= 0) { MC_SPMM(false, true); } else { MC_SPMM(false, false); }
+            switch (mode) {
+            case 0: MC_SPMM(false, 0, 8); break;
+            case 1: MC_SPMM(false, 1, 8); break;
+            case 2: MC_SPMM(false, 2, 7); break;
+            case 4: MC_SPMM(false, 1, 7); break;
+            default: MC_SPMM(false, 2, 6); break;
+            }
         }
 #undef MC_SPMM
         run_long_rows(ctx, c, c.ld, nullptr, c.mc_val, Xg, Xh, nsplit, 1.0, 0.0, nullptr, T);
@@ -1742,9 +1927,9 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
         DevCone &c = ctx->cones[0];
         const int G = pick_group(c.ld);
         /* p2 = <D, C D> rides in the product's epilogue when the direction pass already produced q1, q2, p1 */
-        mc_spmm_plain(ctx, ctx->U, ctx->CD, (ctx->epi_done && ctx->spmm_dot) ? SC_P2 : -1);
+        mc_spmm_plain(ctx, ctx->U, ctx->CD, (ctx->epi_done && ctx->spmm_dot > 0) ? SC_P2 : -1);
         ctx->defer_allreduce = true; /* local sums: p1, p2 and the five terms are all-reduced together below */
-        if (ctx->epi_done && ctx->spmm_dot) {
+        if (ctx->epi_done && ctx->spmm_dot > 0) {
         } else if (ctx->epi_done) {
             const double *D = ctx->U, *T = ctx->CD;
             launch_reduce<1>(ctx, ctx->N, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(D[i], T[i], acc[0]); },
@@ -1890,7 +2075,8 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
         tr = ctx->step_tile_rows > 0 ? ctx->step_tile_rows : (int)std::max<int64_t>(NG, std::min<int64_t>(64, 8192 / (c.ld * 8)));
         tr = (tr + NG - 1) / NG * NG;
         const size_t sb = step_bulk_stage_bytes(gram ? 7 : 5, tr, (int)c.ld);
-        nstage = (int)std::min<size_t>(LGPU_STEP_MAX_STAGES, (size_t)(226 * 1024) / sb);
+        /* 227 KB per CTA in all: the ring + 64 bytes of barriers + the reduction tail's static shared memory (< 1 KB) */
+        nstage = (int)std::min<size_t>(LGPU_STEP_MAX_STAGES, (size_t)(225 * 1024) / sb);
         if (ctx->step_stages > 0) nstage = std::min(nstage, ctx->step_stages);
         bulk_smem = (size_t)nstage * sb + 2 * LGPU_STEP_MAX_STAGES * sizeof(uint64_t);
         if (nstage < 2) tr = 0;
@@ -1906,8 +2092,11 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
             sp.accumulate = 0;
             DISPATCH_G(G, {
                 auto kern = k_mc_step_bulk<GG, true>;
-                static bool attr_set = false;
-                if (!attr_set) { CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+                static size_t attr_bytes = 0;
+                if (bulk_smem > attr_bytes) {
+                    CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+                    attr_bytes = bulk_smem;
+                }
                 kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
                                                                ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
                                                                ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo], ctx->partials, ctx->counter,
@@ -1918,8 +2107,11 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
             sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
             DISPATCH_G(G, {
                 auto kern = k_mc_step_bulk<GG, false>;
-                static bool attr_set = false;
-                if (!attr_set) { CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+                static size_t attr_bytes = 0;
+                if (bulk_smem > attr_bytes) {
+                    CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+                    attr_bytes = bulk_smem;
+                }
                 kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
                                                                ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
                                                                ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials, ctx->counter,

@@ -19,6 +19,8 @@
 #include <vector>
 
 #define LGPU_NSCALAR 256
+#define LGPU_MAX_WORLD 16   /* ranks of one node */
+#define LGPU_PEER_RED 16    /* widest scalar pack of the one-shot peer all-reduce */
 #define LGPU_MAX_PARTIAL_BLOCKS 1184 /* 148 SMs x 8 resident CTAs of 256 threads */
 #define LGPU_MAX_REDUCE 12           /* widest fused reduction (k_reduce / grid_reduce_finish) */
 
@@ -77,12 +79,20 @@ enum {
     KC_MC_STEP,     /* MaxCut-type fused: step + gradient + L-BFGS pair + A(RR^T) */
     KC_MC_DIR,      /* fused two-loop passes */
     KC_DENSE,       /* dense-aggregate cones: DMMA SYR2K / SYMM */
+    KC_EXCH,        /* partitioned runs: peer PUT of the halo rows + wait for the sources */
     KC_COUNT
 };
 
 struct ProfRec {
     int cls;
     cudaEvent_t a, b;
+};
+
+/* one per rank, IPC-shared: written by the peers, read by the owner */
+struct PeerBlock {
+    unsigned long long xflag[LGPU_MAX_WORLD];                 /* [src] = last exchange sequence number src completed */
+    unsigned long long aflag[LGPU_MAX_WORLD];                 /* [src] = last all-reduce sequence number src posted */
+    double inbox[2][LGPU_MAX_WORLD][LGPU_PEER_RED];           /* [seq & 1][src][k] */
 };
 
 struct DevCone {
@@ -186,7 +196,20 @@ struct lgpu_ctx {
     int32_t *send_idx = nullptr; /* [send_rows] local row to pack, grouped by destination */
     int32_t *halo_gid = nullptr; /* [halo_rows] global row of each halo row */
     double *sendbuf = nullptr;   /* [send_rows * ld] */
-    double *halo = nullptr;      /* [halo_rows * ld] */
+    double *halo = nullptr;      /* [halo_rows * ld]  (peer mode: [2][halo_rows * ld], alternating per exchange) */
+    /* Peer-memory exchange (DESIGN.md "Multi-GPU"): every rank maps the other ranks' halo buffers and a small
+     * communication block through CUDA IPC; the halo rows are PUT straight into the consumers' buffers by k_put_rows
+     * (NVLink stores), completion is a per-source sequence number in the consumer's block, and the scalar packs are
+     * all-reduced by one small kernel through the peers' inboxes.  Falls back to NCCL when the mapping is unavailable. */
+    bool peer = false;
+    struct PeerBlock *blk = nullptr;              /* this rank's block (device memory, IPC-exported) */
+    struct PeerBlock *peer_blk[LGPU_MAX_WORLD] = {nullptr}; /* [q] = rank q's block as mapped here ([rank] = blk) */
+    double *peer_halo[LGPU_MAX_WORLD] = {nullptr};          /* [q] = rank q's halo allocation as mapped here */
+    std::vector<int64_t> dst_off;                 /* [q] = first row of MY block inside rank q's halo */
+    int64_t peer_halo_rows[LGPU_MAX_WORLD] = {0}; /* [q] = rank q's halo size in rows (its two buffers are that far apart) */
+    unsigned long long xseq = 0, aseq = 0;        /* exchange / all-reduce sequence numbers (same on all ranks) */
+    const double *halo_cur = nullptr;             /* halo buffer the current product reads */
+    unsigned int *put_counter = nullptr;
     /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */
     bool dense_dmma = true;   /* dense-aggregate cones: SYR2K / SYMM on the FP64 tensor pipe */
     bool fast_enabled = true;
@@ -197,7 +220,7 @@ struct lgpu_ctx {
     /* carried inner products of the two L-BFGS pairs and the current gradient (fused path, history length 2) */
     int step_variant = 1; /* min CTAs/SM of k_mc_step: 0 -> 2, 1 -> 3 (default; measured best: 80 registers, no spills), 2 -> 4, 3 -> 5 */
     bool gram_enabled = true;
-    bool spmm_dot = true;   /* <D, C D> in the sparse product's epilogue (LORADS_SPMM_DOT=0: separate pass, for A/B) */
+    int spmm_dot = 3;       /* <D, C D> in the sparse product's epilogue: 0 separate pass; 1..4 kernel variants (A/B) */
     int step_bulk = 1;      /* k_mc_step through the bulk-copy pipeline (LORADS_STEP_BULK=0: register-staged kernel) */
     int step_tile_rows = 0, step_stages = 0; /* 0: chosen from ld (LORADS_STEP_TILE / LORADS_STEP_STAGES override) */
     bool gram_valid = false;

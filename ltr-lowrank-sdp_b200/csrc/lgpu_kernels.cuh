@@ -653,15 +653,19 @@ __global__ void __launch_bounds__(256) k_gram_finish(int nchunks, int ntile2, in
  * flight per lane needed 48-115 registers and ran 1.8-3.9x slower than this 32-register form at 8 CTAs per SM.
  * A group of G lanes owns a row; lane c holds 16-byte column word c; U entries are fetched per trip. */
 /* DOT: the product's epilogue also accumulates sum_i <X_i, T_i> = <C, X X^T> (the line search's p2 with X = D,
- * lorads_alm.c:714-734).  Row i's own X words are re-read right after the walk that (on a MaxCut row, through the diagonal
- * entry) just gathered them, i.e. from L1/L2: at most F extra bytes instead of the 2 F of a separate <D, T> pass.
- * (Capturing them inside the walk instead cost 120 bytes of spills at the 32 registers that 8 CTAs per SM allow.) */
-template <int G, int U, bool HALO, bool DOT>
-__global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
-                                                         const int32_t *__restrict__ fcol, const double *__restrict__ fval,
-                                                         const double *__restrict__ Xin, const double *__restrict__ Xhalo,
-                                                         int nsplit, int ld, double *__restrict__ T, int64_t self_off,
-                                                         double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec)
+ * lorads_alm.c:714-734).  The layout puts a row's diagonal entry last, so the last factor row the walk gathers IS row
+ * i's own: it serves both the product and the dot, and the separate 2 F pass over (D, T) disappears at no extra
+ * traffic.  (Measured alternatives: re-reading the own row after the walk cost as much as the pass it replaced, 0.7 ms
+ * at C5; capturing it inside the walk by a column compare spilled 120 bytes at the 32 registers 8 CTAs per SM allow.) */
+/* DOT 0: product only.  DOT 1: the diagonal entry is peeled off the walk (one look at the row's last column id first).
+ * DOT 2: plain walk over all entries that remembers the last gathered words and their column; the own row is that one
+ * when the column matches, else one more load.  MINB = CTAs per SM the register budget is cut for (8 -> 32 registers). */
+template <int G, int U, bool HALO, int DOT, int MINB>
+__global__ void __launch_bounds__(LGPU_TPB, MINB) k_mc_spmm(int64_t n, const int32_t *__restrict__ fptr,
+                                                            const int32_t *__restrict__ fcol, const double *__restrict__ fval,
+                                                            const double *__restrict__ Xin, const double *__restrict__ Xhalo,
+                                                            int nsplit, int ld, double *__restrict__ T, int64_t self_off,
+                                                            double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec)
 {
     /* HALO: column ids < nsplit address this rank's own rows (Xin), the others the received halo rows; Xhalo is
      * passed pre-offset by -nsplit rows so both cases index with the column id itself */
@@ -674,10 +678,14 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
     for (int64_t i = g0; i < n; i += groups) {
         const int e0 = fptr[i], e1 = fptr[i + 1];
         if (e1 - e0 > LGPU_LONG_ROW) continue; /* hub rows go to k_spmm_long_chunks */
+        /* DOT 1: the row's diagonal entry, if it has one, is its LAST entry (lgpu_layout.h) */
+        const int ew = (DOT == 1 && e1 > e0 && fcol[e1 - 1] == (int)i + (int)self_off) ? e1 - 1 : e1;
         for (int c = lane; c < ld2; c += G) {
             double2 acc = make_double2(0.0, 0.0);
+            double2 xl = make_double2(0.0, 0.0);
+            int cl = -1;
             int e = e0;
-            for (; e + U <= e1; e += U) {
+            for (; e + U <= ew; e += U) {
                 double2 x[U];
                 double v[U];
 #pragma unroll
@@ -685,22 +693,30 @@ __global__ void __launch_bounds__(LGPU_TPB, 8) k_mc_spmm(int64_t n, const int32_
                     v[u] = fval[e + u];
                     const int col = fcol[e + u];
                     x[u] = reinterpret_cast<const double2 *>(X_ROW(col))[c];
+                    if (DOT == 2 && u == U - 1) cl = col;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) { acc.x = fma(v[u], x[u].x, acc.x); acc.y = fma(v[u], x[u].y, acc.y); }
+                if (DOT == 2) xl = x[U - 1];
             }
-            for (; e < e1; ++e) {
+            for (; e < ew; ++e) {
                 const double v = fval[e];
                 const int col = fcol[e];
                 const double2 x = reinterpret_cast<const double2 *>(X_ROW(col))[c];
                 acc.x = fma(v, x.x, acc.x); acc.y = fma(v, x.y, acc.y);
+                if (DOT == 2) { xl = x; cl = col; }
             }
-            reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
-            if (DOT) {
-                /* the row's own X words: on a MaxCut row they were just gathered for the diagonal entry (an L1/L2 hit) */
-                const double2 xd = reinterpret_cast<const double2 *>(Xin + (size_t)(i + self_off) * ld)[c];
+            if (DOT == 1) {
+                /* the row's own words: the last gathered row when the diagonal is present, else one more load */
+                const double2 xd = reinterpret_cast<const double2 *>(Xin + (size_t)((int)i + (int)self_off) * ld)[c];
+                if (ew < e1) { const double v = fval[ew]; acc.x = fma(v, xd.x, acc.x); acc.y = fma(v, xd.y, acc.y); }
                 dot = fma(xd.x, acc.x, dot); dot = fma(xd.y, acc.y, dot);
             }
+            if (DOT == 2) {
+                if (cl != (int)i + (int)self_off) xl = reinterpret_cast<const double2 *>(Xin + (size_t)((int)i + (int)self_off) * ld)[c];
+                dot = fma(xl.x, acc.x, dot); dot = fma(xl.y, acc.y, dot);
+            }
+            reinterpret_cast<double2 *>(T + (size_t)i * ld)[c] = acc;
         }
     }
 #undef X_ROW
@@ -885,6 +901,109 @@ __global__ void __launch_bounds__(LGPU_TPB) k_pack_rows(int64_t nrows, int ld, c
         const size_t src = (size_t)idx[k] * ld2, dst = (size_t)k * ld2;
         for (int c = lane; c < ld2; c += G)
             reinterpret_cast<double2 *>(out)[dst + c] = reinterpret_cast<const double2 *>(X)[src + c];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Peer-memory exchange over NVLink (one process per GPU, buffers mapped through CUDA IPC).
+ * ------------------------------------------------------------------------------------------------*/
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+/* wait until *flag >= seq; a peer that never arrives is a failed run, not a hung GPU: trap after 30 s */
+__device__ __forceinline__ void wait_flag_ge(const unsigned long long *flag, unsigned long long seq)
+{
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_volatile_u64(flag) < seq) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > 30000000000ull) __trap();
+    }
+}
+
+/* PUT: row idx[k] of X goes to row (k - send_off[q]) of dst[q], q = the destination whose segment holds k -- the pack
+ * kernel and the send/receive pair in one pass of NVLink stores; the last CTA publishes `seq` in every peer's block.
+ * reference: none (the reference is single-process); replaces k_pack_rows + ncclSend/ncclRecv */
+struct PeerPut {
+    int world, rank;
+    long long send_off[LGPU_MAX_WORLD + 1];
+    double *dst[LGPU_MAX_WORLD];
+    unsigned long long *flag[LGPU_MAX_WORLD]; /* &peer_blk[q]->xflag[rank] */
+};
+template <int G>
+__global__ void __launch_bounds__(LGPU_TPB) k_put_rows(int64_t nrows, int ld, const int32_t *__restrict__ idx,
+                                                       const double *__restrict__ X, PeerPut pp, unsigned long long seq,
+                                                       unsigned int *counter)
+{
+    const int lane = threadIdx.x % G;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int ld2 = ld >> 1;
+    for (int64_t k = g0; k < nrows; k += groups) {
+        int q = 0;
+        while (k >= pp.send_off[q + 1]) ++q;
+        const double2 *src = reinterpret_cast<const double2 *>(X) + (size_t)idx[k] * ld2;
+        double2 *dst = reinterpret_cast<double2 *>(pp.dst[q]) + (size_t)(k - pp.send_off[q]) * ld2;
+        for (int c = lane; c < ld2; c += G) dst[c] = src[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (last) {
+            *counter = 0u;
+            __threadfence_system();
+            for (int q = 0; q < pp.world; ++q)
+                if (q != pp.rank) st_release_sys_u64(pp.flag[q], seq);
+        }
+    }
+}
+/* the consumer side: one lane per source spins on this rank's own block until every source has published `seq` */
+__global__ void __launch_bounds__(32) k_wait_sources(const unsigned long long *xflag, int world, int rank, unsigned long long seq)
+{
+    const int q = threadIdx.x;
+    if (q < world && q != rank) wait_flag_ge(xflag + q, seq);
+    __threadfence_system();
+}
+
+/* One-shot all-reduce of `count` (<= LGPU_PEER_RED) device scalars: every rank stores its values into every rank's inbox
+ * (its own included), publishes `seq`, waits for the others and adds the world's values in RANK ORDER -- the same
+ * bits on every rank.  Replaces a latency-bound ncclAllReduce of a few doubles. */
+struct PeerRed {
+    int world, rank;
+    PeerBlock *blk[LGPU_MAX_WORLD]; /* [q] = rank q's block as mapped here */
+};
+__global__ void __launch_bounds__(LGPU_MAX_WORLD * LGPU_PEER_RED) k_peer_allreduce(double *dsc, int first, int count, PeerRed pr,
+                                                                                   unsigned long long seq)
+{
+    const int t = threadIdx.x, q = t / LGPU_PEER_RED, k = t % LGPU_PEER_RED;
+    const int par = (int)(seq & 1ull);
+    if (q < pr.world && k < count) pr.blk[q]->inbox[par][pr.rank][k] = dsc[first + k];
+    __threadfence_system();
+    __syncthreads();
+    if (t < pr.world && t != pr.rank) {
+        st_release_sys_u64(&pr.blk[t]->aflag[pr.rank], seq);
+        wait_flag_ge(&pr.blk[pr.rank]->aflag[t], seq);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < count) {
+        double s = 0.0;
+        const volatile double *in = &pr.blk[pr.rank]->inbox[par][0][0];
+        for (int r = 0; r < pr.world; ++r) s += in[r * LGPU_PEER_RED + t];
+        dsc[first + t] = s;
     }
 }
 

@@ -232,6 +232,7 @@ struct ConeLayout {
     bool partitioned = false, use_halo = false;
     int64_t lo = 0, hi = 0, rows_per_rank = 0, halo_rows = 0, send_rows = 0;
     std::vector<int64_t> send_off, send_cnt, recv_off, recv_cnt; /* per peer, in rows */
+    std::vector<int64_t> dst_off;  /* per peer q: first row of THIS rank's block inside q's halo (= q's recv_off[rank]) */
     std::vector<int32_t> send_idx, halo_gid;
     std::vector<int32_t> lf_ptr, lf_col, lrc_ptr, lrc_gid;
     std::vector<double> lmc_val, lrc_a;
@@ -239,7 +240,7 @@ struct ConeLayout {
 
 /* returns 0, or 1 with a message in err */
 static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int64_t *idx_in, const double *val_in, int world,
-                             int rank, bool single_cone_no_lp, ConeLayout &L, std::string &err)
+                             int rank, bool single_cone_no_lp, ConeLayout &L, std::string &err, bool force_halo = false)
 {
     const int64_t tri = n * (n + 1) / 2;
     const int64_t total = beg[m + 1];
@@ -524,7 +525,23 @@ static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int
     }
     lap("full CSR");
     if (diag_only) {
-        /* fused path layout: C's value per full-CSR entry; row -> constraints, stable in constraint order */
+        /* fused path layout.  The diagonal entry of every CSR row goes LAST (the others stay sorted by column): the
+         * sparse product's walk then ends on the row's own factor row, which is exactly what its <X_i, (C X)_i> epilogue
+         * needs -- no extra load, no compare inside the walk (k_mc_spmm). */
+        par_ranges(T, n, [&](int, int64_t lo, int64_t hi) {
+            for (int64_t j = lo; j < hi; ++j) {
+                const int32_t b = f_ptr[j], e = f_ptr[j + 1];
+                for (int32_t q = b; q < e - 1; ++q)
+                    if (f_col[q] == (int32_t)j) {
+                        const int32_t sl = f_slot[q];
+                        for (int32_t t = q; t < e - 1; ++t) { f_col[t] = f_col[t + 1]; f_slot[t] = f_slot[t + 1]; }
+                        f_col[e - 1] = (int32_t)j;
+                        f_slot[e - 1] = sl;
+                        break;
+                    }
+            }
+        });
+        /* C's value per full-CSR entry; row -> constraints, stable in constraint order */
         L.mc_val.resize(L.nnzF);
         par_ranges(T, L.nnzF, [&](int, int64_t lo, int64_t hi) { for (int64_t e = lo; e < hi; ++e) L.mc_val[e] = cval[f_slot[e]]; });
         L.rc_ptr.assign(n + 1, 0);
@@ -604,6 +621,7 @@ static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int
     {
         int64_t all_halo = 0;
         std::vector<uint8_t> seen(n);
+        L.dst_off.assign(P, 0);
         for (int q = 0; q < P; ++q) {
             int64_t qlo, qhi, qr;
             lgpu_partition_rows(n, P, q, &qlo, &qhi, &qr);
@@ -612,9 +630,17 @@ static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int
                 const int32_t j = f_col[e];
                 if ((j < qlo || j >= qhi) && !seen[j]) { seen[j] = 1; ++all_halo; }
             }
+            /* q's halo lists its sources in rank order: my block starts after the rows q references below my first row
+             * (q's own rows are not marked) */
+            if (q != rank) {
+                int64_t before = 0;
+                for (int64_t j = 0; j < lo; ++j) before += seen[j];
+                L.dst_off[q] = before;
+            }
         }
         L.use_halo = (double)all_halo < 0.85 * (double)n * (double)(P - 1);
     }
+    if (force_halo) L.use_halo = true;
     if (const char *hv = getenv("LORADS_HALO")) L.use_halo = atoi(hv) != 0;
     if (L.use_halo) {
         for (auto &cj : L.lf_col) cj = remap[cj];

@@ -115,6 +115,7 @@ def lib() -> ctypes.CDLL:
         "lgpu_alm_inner_update": (i, [_vp, d, d, _c_dp, _c_dp]),
         "lgpu_set_fused_path": (i, [_vp, i]),
         "lgpu_uses_fused_path": (i, [_vp]),
+        "lgpu_uses_peer_exchange": (i, [_vp]),
         "lgpu_set_carried_dots": (i, [_vp, i]),
         "lgpu_set_dense_tensor_path": (i, [_vp, i]),
         "lgpu_lbfgs_push": (i, [_vp, d]),
@@ -331,6 +332,9 @@ class Context:
         """join the NCCL communicator of a row-block partitioned run (before load())"""
         assert len(unique_id) == 128
         self._ck(self._L.lgpu_comm_init(self._h, unique_id, int(rank), int(world)), "lgpu_comm_init")
+
+    def uses_peer_exchange(self) -> bool:
+        return bool(self._L.lgpu_uses_peer_exchange(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -17,12 +17,12 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     ("r1 kernels (register step, separate <D,T>)", {"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0"}),
-    ("register step + dot in product", {"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "1"}),
-    ("bulk step default", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"}),
-    ("bulk step tile16 x4", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1", "LORADS_STEP_TILE": "16", "LORADS_STEP_STAGES": "4"}),
-    ("bulk step tile16 x3", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1", "LORADS_STEP_TILE": "16", "LORADS_STEP_STAGES": "3"}),
-    ("bulk step tile32 x2", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1", "LORADS_STEP_TILE": "32", "LORADS_STEP_STAGES": "2"}),
-    ("bulk step tile48 x2", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1", "LORADS_STEP_TILE": "48", "LORADS_STEP_STAGES": "2"}),
+    ("bulk step, separate <D,T>", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "0"}),
+    ("bulk step, dot mode 1 (peeled diagonal, 8 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"}),
+    ("bulk step, dot mode 2 (last gathered row, 7 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "2"}),
+    ("bulk step, dot mode 3 (last gathered row, 6 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "3"}),
+    ("bulk step, dot mode 4 (peeled diagonal, 7 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "4"}),
+    ("bulk step tile24 x4, separate <D,T>", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "0", "LORADS_STEP_TILE": "24", "LORADS_STEP_STAGES": "4"}),
 ]
 KEYS = ["LORADS_STEP_BULK", "LORADS_SPMM_DOT", "LORADS_STEP_TILE", "LORADS_STEP_STAGES", "LORADS_STEP_VARIANT"]
 

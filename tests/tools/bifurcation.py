@@ -35,10 +35,19 @@ CASES = [
 ]
 
 def summary(out):
-    res = {"alm_inner": None, "admm": None, "obj": None, "status": None}
+    res = {"alm_inner": None, "admm": None, "obj": None, "status": None, "rank_first": None, "rank_last": None}
     for line in out.splitlines():
         if "OuterIter:" in line and "InnerIter:" in line:
             res["alm_inner"] = int(line.split("InnerIter:")[1].split()[0])
+            res["rank_last"] = int(line.split("CurrRank:")[1].split()[0])
+            if res["rank_first"] is None:
+                res["rank_first"] = res["rank_last"]
+        elif "2.Dual Objective:" in line:
+            res["dobj"] = float(line.split(":")[-1])
+        elif "1.Constraint Violation(1)" in line:
+            res["constr_vio_l1"] = float(line.split(":")[-1])
+        elif "3.Primal Dual Gap" in line:
+            res["pd_gap"] = float(line.split(":")[-1])
         elif line.startswith("ADMM Iter:"):
             res["admm"] = int(line.split("Iter:")[1].split()[0]) + 1
         elif "1.Primal Objective:" in line:
