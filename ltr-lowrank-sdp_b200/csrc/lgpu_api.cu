@@ -154,7 +154,7 @@ template <class F> static void launch_scalar(lgpu_ctx *ctx, F f);
 template <int K, class F, class P>
 static void launch_reduce_post(lgpu_ctx *ctx, int64_t n, F f, SlotSpec<K> spec, P post, int cls = KC_REDUCE)
 {
-    if (ctx->world > 1 && !ctx->defer_allreduce) {
+    if (ctx->world > 1 && !ctx->defer_allreduce && !ctx->cone_par) { /* by-cone mode: flat vectors are replicated */
         {
             Prof pr(ctx, cls);
             k_reduce<K, F, NoPost><<<grid_for(ctx, n > 0 ? n : 1, (const void *)k_reduce<K, F, NoPost>), LGPU_TPB, 0, ctx->stream>>>(
@@ -463,7 +463,7 @@ struct Owned {
 };
 static Owned owned(const lgpu_ctx *ctx)
 {
-    if (ctx->world > 1) return {ctx->cones[0].m_loc, ctx->cones[0].rc_gid};
+    if (ctx->world > 1 && !ctx->cone_par) return {ctx->cones[0].m_loc, ctx->cones[0].rc_gid};
     return {ctx->m, nullptr};
 }
 static inline int pick_group(int64_t ld)
@@ -622,6 +622,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     ctx->device = device;
     if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
     if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
+    if (const char *v = getenv("LORADS_FUSE_PUT")) ctx->fuse_put = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
     if (const char *v = getenv("LORADS_STEP_STAGES")) ctx->step_stages = atoi(v);
     if (const char *v = getenv("LORADS_SPMM_DOT")) ctx->spmm_dot = atoi(v);
@@ -736,7 +737,7 @@ extern "C" void lgpu_destroy(lgpu_ctx *ctx)
     free_vars(ctx, false);
     for (int q = 0; q < ctx->world; ++q)
         if (ctx->peer && q != ctx->rank && ctx->peer_blk[q]) cudaIpcCloseMemHandle(ctx->peer_blk[q]);
-    dev_free(ctx->blk); dev_free(ctx->put_counter);
+    dev_free(ctx->blk); dev_free(ctx->put_counter); dev_free(ctx->put_dest);
     dev_free(ctx->b); dev_free(ctx->lam); dev_free(ctx->cvs); dev_free(ctx->q1); dev_free(ctx->q2); dev_free(ctx->M1);
     dev_free(ctx->mtmp);
     dev_free(ctx->lp.obj); dev_free(ctx->lp.r_ptr); dev_free(ctx->lp.r_col); dev_free(ctx->lp.r_val);
@@ -953,6 +954,9 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         if (build_cone_layout(n, m, beg, idx_in, val_in, ctx->world, ctx->rank, ctx->ncones == 1 && ctx->lp.n == 0, L, err, ctx->peer))
             LGPU_FAIL(ctx, "%s", err.c_str());
     }
+    /* more than one GPU and not the single MaxCut-type cone the row-block partition handles: by-cone partition (every
+     * rank keeps every cone and every vector; the operator work of a cone is done by its owner, see cone_* helpers) */
+    if (ctx->world > 1 && !L.partitioned) ctx->cone_par = true;
     free_cone(c);
     c.obj_type = L.obj_type;
     c.mA = L.mA;
@@ -981,6 +985,20 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         ctx->send_rows = L.send_rows;
         ctx->use_halo = L.use_halo;
         ctx->dst_off = L.dst_off;
+        dev_free(ctx->put_dest);
+        if (ctx->peer && L.use_halo && ctx->world > 1) {
+            /* per own row and peer: the row's place in that peer's halo, or -1 (k_mc_combine<PUT>) */
+            const int np = ctx->world - 1;
+            const int64_t nl = L.hi - L.lo;
+            std::vector<int32_t> dest((size_t)nl * np, -1);
+            for (int q = 0, j = 0; q < ctx->world; ++q) {
+                if (q == ctx->rank) continue;
+                for (int64_t k = 0; k < L.send_cnt[q]; ++k)
+                    dest[(size_t)L.send_idx[L.send_off[q] + k] * np + j] = (int32_t)(L.dst_off[q] + k);
+                ++j;
+            }
+            TRY(dev_upload(ctx, &ctx->put_dest, dest));
+        }
         if (L.use_halo) {
             dev_free(ctx->send_idx);
             TRY(dev_upload(ctx, &ctx->send_idx, L.send_idx));
@@ -1224,12 +1242,28 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     ctx->gram_valid = false;
     ctx->gram_pair_ok[0] = ctx->gram_pair_ok[1] = false;
     ctx->epi_done = false;
-    if (ctx->world > 1 && !ctx->mc) LGPU_FAIL(ctx, "partitioned runs use the fused MaxCut-type path only");
+    if (ctx->world > 1 && !ctx->mc && !ctx->cone_par) LGPU_FAIL(ctx, "partitioned runs use the fused MaxCut-type path only");
+    if (ctx->cone_par) {
+        if (ctx->mc) LGPU_FAIL(ctx, "internal: by-cone partition with the fused single-cone path");
+        /* owner of every cone: greedy balance of the per-iteration operator work ~ (nnz of the pattern + of the constraints)
+         * x rank, largest cone first; the same map on every rank */
+        std::vector<int> order(ctx->ncones);
+        std::iota(order.begin(), order.end(), 0);
+        auto cost = [&](int k) { const DevCone &d = ctx->cones[k]; return (double)(d.nnzP + d.nnzA + d.n) * (double)std::max<int64_t>(d.ld, 1); };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+        std::vector<double> load(ctx->world, 0.0);
+        ctx->cone_owner.assign(ctx->ncones, 0);
+        for (int k : order) {
+            const int q = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            ctx->cone_owner[k] = q;
+            load[q] += cost(k);
+        }
+    }
     if (ctx->mc) {
         TRY(alloc_flat(ctx, &ctx->CR));
         TRY(alloc_flat(ctx, &ctx->CD));
     }
-    if (ctx->world > 1) {
+    if (ctx->world > 1 && !ctx->cone_par) {
         dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
         if (ctx->use_halo && ctx->peer) {
             /* two halo buffers, used alternately: a fast peer may already PUT the next exchange's rows while this rank's
@@ -1411,7 +1445,7 @@ extern "C" int lgpu_get_vec(lgpu_ctx *ctx, int which, double *v)
 {
     if (!ctx || !mvec_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
-    if (ctx->world > 1 && which != LGPU_VEC_B) {
+    if (ctx->world > 1 && !ctx->cone_par && which != LGPU_VEC_B) {
         /* every constraint is owned by exactly one rank: owned entries into a zeroed vector, summed over the ranks */
         double *tmp = ctx->mtmp;
         const double *src = mvec_of(ctx, which);
@@ -1531,6 +1565,18 @@ static int mc_exchange(lgpu_ctx *ctx, const double *X)
     }
     DevCone &c = ctx->cones[0];
     const int G = pick_group(c.ld);
+    if (ctx->peer && ctx->pending_put_x == X && ctx->pending_put_seq == ctx->xseq) {
+        /* the direction pass already PUT these rows (k_mc_combine<PUT>): only wait for the rows of the sources */
+        const unsigned long long seq = ctx->pending_put_seq;
+        ctx->pending_put_x = nullptr;
+        {
+            Prof pr(ctx, KC_EXCH);
+            k_wait_sources<<<1, 32, 0, ctx->stream>>>(ctx->blk->xflag, ctx->world, ctx->rank, seq);
+        }
+        ctx->halo_cur = ctx->halo + (size_t)(seq & 1ull) * (size_t)std::max<int64_t>(ctx->halo_rows, 1) * (size_t)c.ld;
+        return 0;
+    }
+    ctx->pending_put_x = nullptr;
     if (ctx->peer) {
         /* PUT the rows every peer's CSR references straight into its halo buffer, then wait for the sources of mine */
         const unsigned long long seq = ++ctx->xseq;
@@ -1665,10 +1711,37 @@ static void pair_ptrs(lgpu_ctx *ctx, int pair, double **A, double **B)
     }
 }
 
+/* ---- by-cone partition (several GPUs, problem not of the single MaxCut-type form) ---------------------------------
+ * Cones couple only through the m-vector constrValSum and through scalars (lorads_alg_common.c:221-229), so: every rank
+ * keeps all cones and all flat vectors (replicated, and updated by the same deterministic kernels on every rank); the
+ * OPERATOR work of a cone -- UVt, the constraint gathers, A^*(w), S X, the CG solves -- is done by the cone's owner
+ * only; what the others need is summed over the ranks: the length-m constraint values (ncclAllReduce), the objective
+ * scalars, the gradient segments (non-owners contribute zeros, so the sum is the owner's value bit for bit). */
+static inline bool cone_mine(const lgpu_ctx *ctx, const DevCone &c)
+{
+    return !ctx->cone_par || ctx->cone_owner[(size_t)(&c - ctx->cones.data())] == ctx->rank;
+}
+/* terms every rank would add (LP block, replicated m-vector parts) are added by rank 0 only when the result is summed */
+static inline bool cone_lead(const lgpu_ctx *ctx) { return !ctx->cone_par || ctx->rank == 0; }
+static int cone_allreduce(lgpu_ctx *ctx, double *p, size_t count)
+{
+    if (!ctx->cone_par || count == 0) return 0;
+    NC(ctx, g_nccl.AllReduce(p, p, count, LG_NCCL_FLOAT64, LG_NCCL_SUM, (lg_ncclComm_t)ctx->comm, ctx->stream));
+    return 0;
+}
+/* make `count` doubles at p, valid on `owner`, valid everywhere: zeros elsewhere + sum */
+static int cone_bcast(lgpu_ctx *ctx, double *p, size_t count, int owner)
+{
+    if (!ctx->cone_par || count == 0) return 0;
+    if (ctx->rank != owner) CU(ctx, cudaMemsetAsync(p, 0, sizeof(double) * count, ctx->stream));
+    return cone_allreduce(ctx, p, count);
+}
+
 /* per cone: uvt on the pattern, cv = A_c(.), optional objective accumulate (LORADSInitConstrValObjVal) */
 static void cones_auv(lgpu_ctx *ctx, const double *A, const double *B, int obj_slot /* -1: none */)
 {
     for (auto &c : ctx->cones) {
+        if (!cone_mine(ctx, c)) continue;
         run_uvt(ctx, c, c.ld, A + c.off, B + c.off, c.uvt);
         if (obj_slot >= 0) run_obj_gather(ctx, c, c.uvt, obj_slot, 1);
         run_con_gather(ctx, c, c.uvt, c.cv);
@@ -1679,13 +1752,13 @@ static void cones_auv(lgpu_ctx *ctx, const double *A, const double *B, int obj_s
 static void sum_constr_vals(lgpu_ctx *ctx, const double *A, const double *B, double scale, double *out)
 {
     const int64_t m = ctx->m;
-    if (ctx->lp.n == 0 && ctx->ncones == 1 && ctx->cones[0].mA == m) {
+    if (!ctx->cone_par && ctx->lp.n == 0 && ctx->ncones == 1 && ctx->cones[0].mA == m) {
         /* one cone in which every constraint is non-zero: its compact constrVal IS the m-vector (con_gid = identity) */
         const double *cv = ctx->cones[0].cv;
         launch_map(ctx, m, [=] __device__(int64_t i) { out[i] = 0.0 + scale * cv[i]; });
         return;
     }
-    if (ctx->lp.n > 0) {
+    if (ctx->lp.n > 0 && cone_lead(ctx)) {
         const int32_t *rp = ctx->lp.r_ptr, *rc = ctx->lp.r_col;
         const double *rv = ctx->lp.r_val;
         const double *u = A + ctx->lp.off, *v = B + ctx->lp.off;
@@ -1698,10 +1771,12 @@ static void sum_constr_vals(lgpu_ctx *ctx, const double *A, const double *B, dou
         cudaMemsetAsync(out, 0, sizeof(double) * m, ctx->stream);
     }
     for (auto &c : ctx->cones) {
+        if (!cone_mine(ctx, c)) continue;
         const int32_t *gid = c.con_gid;
         const double *cv = c.cv;
         launch_map(ctx, c.mA, [=] __device__(int64_t t) { out[gid[t]] += scale * cv[t]; });
     }
+    cone_allreduce(ctx, out, (size_t)m); /* by-cone partition: the length-m constraint values are summed over the owners */
 }
 
 extern "C" int lgpu_init_constr_val(lgpu_ctx *ctx, int pair)
@@ -1725,9 +1800,14 @@ extern "C" int lgpu_init_constr_val(lgpu_ctx *ctx, int pair)
 static void grad_from_m1(lgpu_ctx *ctx)
 {
     for (auto &c : ctx->cones) {
+        if (!cone_mine(ctx, c)) {
+            cudaMemsetAsync(ctx->G + c.off, 0, sizeof(double) * (size_t)(c.n_alloc * c.ld), ctx->stream);
+            continue;
+        }
         run_wsum(ctx, c, ctx->M1, true, true, 1.0, c.S);
         run_spmm(ctx, c, c.ld, c.S, ctx->R + c.off, 2.0, 0.0, nullptr, ctx->G + c.off);
     }
+    cone_allreduce(ctx, ctx->G, (size_t)ctx->lp.off); /* the owners' gradient segments, exact (the others hold zeros) */
     if (ctx->lp.n > 0) {
         /* ALMSetGradLP (lorads_alm.c:89-113): grad_j = 2 (c_j + a_j^T M1) r_j */
         const int32_t *cp = ctx->lp.c_ptr, *cr = ctx->lp.c_row;
@@ -1825,11 +1905,34 @@ static int mc_direction_gram(lgpu_ctx *ctx, int nn)
     if (!ctx->cr_valid) mc_refresh_cr(ctx);
     const int G = pick_group(c.ld);
     ctx->defer_allreduce = true; /* <C R, D> joins the seven line-search terms' all-reduce */
+    PeerDirect pd;
+    memset(&pd, 0, sizeof(pd));
+    const bool put = ctx->peer && ctx->use_halo && ctx->fuse_put && ctx->put_dest != nullptr;
+    if (put) {
+        /* the halo exchange of D rides inside this pass; the sparse product that follows only waits for its sources */
+        const unsigned long long seq = ++ctx->xseq;
+        pd.npeer = ctx->world - 1;
+        pd.seq = seq;
+        for (int q = 0, j = 0; q < ctx->world; ++q) {
+            if (q == ctx->rank) continue;
+            pd.dst[j] = ctx->peer_halo[q] + (size_t)(seq & 1ull) * (size_t)std::max<int64_t>(ctx->peer_halo_rows[q], 1) * (size_t)c.ld;
+            pd.flag[j] = &ctx->peer_blk[q]->xflag[ctx->rank];
+            ++j;
+        }
+        ctx->pending_put_x = ctx->U;
+        ctx->pending_put_seq = seq;
+    }
     {
         Prof pr(ctx, KC_MC_DIR);
-        DISPATCH_G(G, k_mc_combine<GG><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG>), LGPU_TPB, 0, ctx->stream>>>(
-                          c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], ctx->R, ctx->CR, ctx->U, c.rc_ptr,
-                          c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0)));
+        if (put) {
+            DISPATCH_G(G, k_mc_combine<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
+                              c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], ctx->R, ctx->CR, ctx->U, c.rc_ptr,
+                              c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0), ctx->put_dest, pd));
+        } else {
+            DISPATCH_G(G, k_mc_combine<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
+                              c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], ctx->R, ctx->CR, ctx->U, c.rc_ptr,
+                              c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0), nullptr, pd));
+        }
     }
     ctx->defer_allreduce = false;
     ctx->epi_done = true;
@@ -1948,13 +2051,13 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
     launch_scalar(ctx, [=] __device__() { dsc[SC_P1] = 0.0; dsc[SC_P2] = 0.0; });
     /* ALMCalq12p12: q1 = 2 A(sym(R D^T)), p1 = 2 <C, R D^T>; q2 = A(D D^T), p2 = <C, D D^T> */
     cones_auv(ctx, ctx->R, ctx->U, SC_P1);
-    if (ctx->lp.n > 0) {
+    if (ctx->lp.n > 0 && cone_lead(ctx)) {
         const double *obj = ctx->lp.obj, *u = ctx->R + ctx->lp.off, *v = ctx->U + ctx->lp.off;
         launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * v[j], acc[0]); }, slot1(SC_P1, 1));
     }
     sum_constr_vals(ctx, ctx->R, ctx->U, 2.0, ctx->q1);
     cones_auv(ctx, ctx->U, ctx->U, SC_P2);
-    if (ctx->lp.n > 0) {
+    if (ctx->lp.n > 0 && cone_lead(ctx)) {
         const double *obj = ctx->lp.obj, *u = ctx->U + ctx->lp.off;
         launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * u[j], acc[0]); }, slot1(SC_P2, 1));
     }
@@ -1981,7 +2084,9 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
             acc[4] = fma(q0, a, acc[4]);
         }, sp);
         ctx->defer_allreduce = false;
-        TRY(allreduce_scalars(ctx, SC_P1, 7));
+        /* row blocks: all seven are partial sums; by cone: only the two objective terms are (the five m-vector terms were
+         * formed from replicated vectors) */
+        TRY(allreduce_scalars(ctx, SC_P1, ctx->cone_par ? 2 : 7));
     }
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_P1, 7));
@@ -2249,14 +2354,16 @@ extern "C" int lgpu_cal_obj(lgpu_ctx *ctx, int admm, double *pobj)
         return 0;
     }
     launch_scalar(ctx, [=] __device__() { dsc[SC_OBJ] = 0.0; });
-    if (ctx->lp.n > 0) {
+    if (ctx->lp.n > 0 && cone_lead(ctx)) {
         const double *obj = ctx->lp.obj, *u = ctx->R + ctx->lp.off;
         launch_reduce<1>(ctx, ctx->lp.n, [=] __device__(int64_t j, double(&acc)[1]) { acc[0] = fma(obj[j], u[j] * u[j], acc[0]); }, slot1(SC_OBJ, 1));
     }
     for (auto &c : ctx->cones) {
+        if (!cone_mine(ctx, c)) continue;
         run_uvt(ctx, c, c.ld, ctx->R + c.off, ctx->R + c.off, c.uvt);
         run_obj_gather(ctx, c, c.uvt, SC_OBJ, 1);
     }
+    if (ctx->cone_par) TRY(allreduce_scalars(ctx, SC_OBJ, 1));
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_OBJ, 1));
     *pobj = ctx->hsc[SC_OBJ];
@@ -2496,13 +2603,29 @@ extern "C" int lgpu_admm_update_var(lgpu_ctx *ctx, double rho, double cg_tol, in
     ctx->epi_done = false;
     for (int ci = 0; ci < ctx->ncones; ++ci) {
         DevCone &c = ctx->cones[ci];
-        int64_t it = 0;
-        TRY(admm_update_one(ctx, ci, ctx->U, ctx->V, rho, cg_tol, cg_max_iter, &it));
-        *cg_iter_total += it;
-        refresh_cone_cv(ctx, c);
-        TRY(admm_update_one(ctx, ci, ctx->V, ctx->U, rho, cg_tol, cg_max_iter, &it));
-        *cg_iter_total += it;
-        refresh_cone_cv(ctx, c);
+        /* Gauss-Seidel over the cones, U then V (lorads_alg_common.c:298-326).  By-cone partition: the owner solves and
+         * refreshes the cone's constraint values (only it holds the cone's compact constrVal); the updated segment, the
+         * length-m constrValSum and the CG count reach the others through sums with zeros (exact). */
+        for (int pass = 0; pass < 2; ++pass) {
+            double *upd = pass == 0 ? ctx->U : ctx->V;
+            const double *fixed = pass == 0 ? ctx->V : ctx->U;
+            int64_t it = 0;
+            if (cone_mine(ctx, c)) {
+                TRY(admm_update_one(ctx, ci, upd, fixed, rho, cg_tol, cg_max_iter, &it));
+                refresh_cone_cv(ctx, c);
+            }
+            if (ctx->cone_par) {
+                const int owner = ctx->cone_owner[ci];
+                TRY(cone_bcast(ctx, upd + c.off, (size_t)(c.n_alloc * c.ld), owner));
+                TRY(cone_bcast(ctx, ctx->cvs, (size_t)ctx->m, owner));
+                ctx->hsc[SC_TMP] = ctx->rank == owner ? (double)it : 0.0;
+                CU(ctx, cudaMemcpyAsync(ctx->dsc + SC_TMP, ctx->hsc + SC_TMP, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+                TRY(allreduce_scalars(ctx, SC_TMP, 1));
+                TRY(fetch_scalars(ctx, SC_TMP, 1));
+                it = (int64_t)(ctx->hsc[SC_TMP] + 0.5);
+            }
+            *cg_iter_total += it;
+        }
     }
     CHECK_LAUNCH(ctx);
     if (ctx->lp.n > 0) TRY(admm_lp_sweep(ctx, rho));
@@ -2552,7 +2675,7 @@ extern "C" int lgpu_gram(lgpu_ctx *ctx, int phase, int cone, double *gram)
         k_gram_finish<<<nt * nt, 256, 0, ctx->stream>>>(nchunks, nt * nt, r, part, dg);
     }
     CHECK_LAUNCH(ctx);
-    if (ctx->world > 1)
+    if (ctx->world > 1 && !ctx->cone_par) /* by cone: the factors are replicated, the Gram is already whole */
         NC(ctx, g_nccl.AllReduce(dg, dg, (size_t)r * r, LG_NCCL_FLOAT64, LG_NCCL_SUM, (lg_ncclComm_t)ctx->comm, ctx->stream));
     CU(ctx, cudaMemcpyAsync(gram, dg, gram_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2613,11 +2736,12 @@ static double tridiag_last_component(const std::vector<double> &a, const std::ve
 __global__ void __launch_bounds__(LGPU_TPB) k_lanczos_symv(int64_t n, const int32_t *__restrict__ fp, const int32_t *__restrict__ fc,
                                                            const int32_t *__restrict__ fs, const double *__restrict__ Sv,
                                                            const double *__restrict__ q, const double *__restrict__ qm,
-                                                           double bprev, double *__restrict__ w, double *partials,
-                                                           unsigned int *counter, double *dsc, SlotSpec<1> spec)
+                                                           const double *__restrict__ bprev_p, double *__restrict__ w,
+                                                           double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double bprev = qm ? *bprev_p : 0.0; /* beta_{k-1} stays on the device between read-backs */
     double red[1] = {0.0};
     for (int64_t i = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += warps) {
         double a = 0.0;
@@ -2692,18 +2816,21 @@ __global__ void __launch_bounds__(LGPU_TPB) k_lanczos_symv_part(int64_t nloc, in
  * w = S qk - bprev qm (qm may be null) and dsc[SC_LANCZOS] = <qk, S qk>.  Stop: Ritz residual |beta_k s_k| <= 1e-6 x
  * (spectral scale of T_k).  Small problems keep the whole Krylov basis and re-orthogonalise against it (two launches per
  * step); large ones run the plain three-term recurrence, whose extreme Ritz value stays accurate without it. */
-typedef std::function<int(const double *, const double *, double, double *)> LanczosApply;
+typedef std::function<int(const double *, const double *, const double *, double *)> LanczosApply;
 static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const LanczosApply &apply, double *theta_out)
 {
     double *dsc = ctx->dsc;
     const int kmax = (int)std::min<int64_t>(n, 300);
+    const int batch = 16; /* steps between two read-backs of (alpha, beta) */
     const bool full = (double)vec_len * (double)(kmax + 1) * 8.0 <= 256.0e6;
     const size_t vec = (size_t)vec_len;
     const size_t nvec = full ? (size_t)kmax + 2 : 4;
-    TRY(ensure_dstage(ctx, sizeof(double) * (vec * nvec + (size_t)kmax + 8)));
+    TRY(ensure_dstage(ctx, sizeof(double) * (vec * nvec + 3 * (size_t)kmax + 8)));
     double *Q = (double *)ctx->dstage; /* full: q_0 .. q_kmax ; else ring of 3 */
     double *w = Q + vec * (nvec - 1);
-    double *hbuf = w + vec;
+    double *hbuf = w + vec;            /* [kmax] basis dot products */
+    double *dal = hbuf + kmax + 2;     /* [kmax] alpha_k, on the device until the next read-back */
+    double *dbe = dal + kmax;          /* [kmax] beta_k */
     CU(ctx, cudaMemsetAsync(Q, 0, sizeof(double) * vec * nvec, ctx->stream)); /* padding entries stay zero */
     auto qptr = [&](int k) { return Q + vec * (size_t)(full ? k : (k % 3)); };
     {
@@ -2717,13 +2844,18 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
         }, slot1(SC_LANCZOS));
         launch_map(ctx, n, [=] __device__(int64_t i) { q0[i] /= sqrt(dsc[SC_LANCZOS]); });
     }
-    std::vector<double> al, be;
+    /* The recurrence runs `batch` steps at a time without a host round trip: alpha_k, beta_k and 1 / beta_k are formed
+     * by the finishing thread of the |w|^2 reduction and stay on the device.  After a batch the host reads the new
+     * (alpha, beta) and applies the stopping test to every prefix in order, so the result is the one the step-by-step
+     * test would have returned; the (at most batch - 1) surplus steps cost a few launches. */
+    std::vector<double> al((size_t)kmax), be((size_t)kmax);
     double theta = 0.0;
-    for (int k = 0; k < kmax; ++k) {
+    int checked = 0;
+    bool done = false;
+    for (int k = 0; k < kmax && !done; ++k) {
         const double *qk = qptr(k);
         const double *qm = k > 0 ? qptr(k - 1) : nullptr;
-        const double bprev = k > 0 ? be[k - 1] : 0.0;
-        TRY(apply(qk, qm, bprev, w));
+        TRY(apply(qk, qm, k > 0 ? dbe + (k - 1) : nullptr, w));
         /* w -= alpha_k q_k ; then (small problems) against the whole basis ; beta_k = |w| */
         launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS], qk[i], w[i]); });
         if (full) {
@@ -2736,30 +2868,48 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
                 k_basis_update<<<grid_for(ctx, n, (const void *)k_basis_update), LGPU_TPB, 0, ctx->stream>>>(vec_len, k + 1, Q, hbuf, w);
             }
         }
-        launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); }, slot1(SC_LANCZOS + 1));
-        CHECK_LAUNCH(ctx);
-        TRY(fetch_scalars(ctx, SC_LANCZOS, 2));
-        al.push_back(ctx->hsc[SC_LANCZOS]);
-        const double bnorm = sqrt(ctx->hsc[SC_LANCZOS + 1]);
-        be.push_back(bnorm);
-        theta = tridiag_extreme_eig(al, be, k + 1, -1);
-        const double top = tridiag_extreme_eig(al, be, k + 1, +1);
-        const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
-        const double resid = bnorm * tridiag_last_component(al, be, k + 1, theta);
-        if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale) break;
-        if (k + 1 >= kmax) {
-            /* not converged: a Ritz value is only an UPPER bound of lambda_min, which would under-report the dual
-             * infeasibility; report the residual-corrected value (an eigenvalue lies within `resid` of theta) and say so */
-            if (kmax < n) {
-                fprintf(stderr, "lorads_b200: warning: Lanczos stopped after %d steps with Ritz residual %.3e (scale %.3e); "
-                                "dual infeasibility uses theta - residual\n", kmax, resid, scale);
-                theta -= resid;
-            }
-            break;
+        {
+            double *ak = dal + k, *bk = dbe + k;
+            launch_reduce_post<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); },
+                                  slot1(SC_LANCZOS + 1), [=] __device__(double *sc) {
+                                      const double b = sqrt(sc[SC_LANCZOS + 1]);
+                                      *ak = sc[SC_LANCZOS];
+                                      *bk = b;
+                                      sc[SC_LANCZOS + 3] = b > 0.0 ? 1.0 / b : 0.0; /* an exhausted Krylov space yields zeros, not NaNs */
+                                  });
         }
-        double *qn = qptr(k + 1);
-        const double inv = 1.0 / bnorm;
-        launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * inv; });
+        CHECK_LAUNCH(ctx);
+        if (k + 1 < kmax) {
+            double *qn = qptr(k + 1);
+            launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * dsc[SC_LANCZOS + 3]; });
+        }
+        if ((k + 1) % batch != 0 && k + 1 < kmax) continue;
+        /* read the new coefficients back and test the prefixes checked .. k */
+        CU(ctx, cudaMemcpyAsync(al.data() + checked, dal + checked, sizeof(double) * (size_t)(k + 1 - checked), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        CU(ctx, cudaMemcpyAsync(be.data() + checked, dbe + checked, sizeof(double) * (size_t)(k + 1 - checked), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int j = checked; j <= k; ++j) {
+            const double bnorm = be[(size_t)j];
+            theta = tridiag_extreme_eig(al, be, j + 1, -1);
+            const double top = tridiag_extreme_eig(al, be, j + 1, +1);
+            const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
+            const double resid = bnorm * tridiag_last_component(al, be, j + 1, theta);
+            if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale) { done = true; break; }
+            if (j + 1 >= kmax) {
+                /* not converged: a Ritz value is only an UPPER bound of lambda_min, which would under-report the dual
+                 * infeasibility; report the residual-corrected value (an eigenvalue lies within `resid` of theta) and say so */
+                if (kmax < n) {
+                    fprintf(stderr, "lorads_b200: warning: Lanczos stopped after %d steps with Ritz residual %.3e (scale %.3e); "
+                                    "dual infeasibility uses theta - residual\n", kmax, resid, scale);
+                    theta -= resid;
+                }
+                done = true;
+                break;
+            }
+        }
+        checked = k + 1;
     }
     *theta_out = theta;
     return 0;
@@ -2776,13 +2926,13 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
     if (!ctx || !ctx->vars_ready) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     double total = 0.0;
-    if (ctx->world > 1) {
+    if (ctx->world > 1 && !ctx->cone_par) {
         DevCone &c = ctx->cones[0];
         const int64_t n = c.n_glob, vec_len = (int64_t)ctx->world * c.n_alloc;
         const int32_t *hg = ctx->use_halo ? ctx->halo_gid : nullptr;
         double theta = 0.0;
         ctx->defer_allreduce = true; /* full-length replicated vectors: the reductions below are already global */
-        auto apply = [&](const double *qk, const double *qm, double bprev, double *w) -> int {
+        auto apply = [&](const double *qk, const double *qm, const double *bprev_p, double *w) -> int {
             {
                 Prof pr(ctx, KC_SPMM);
                 k_lanczos_symv_part<<<grid_for(ctx, c.n * 32, (const void *)k_lanczos_symv_part), LGPU_TPB, 0, ctx->stream>>>(
@@ -2793,7 +2943,7 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
             launch_reduce<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
                 const double a = w[i];
                 acc[0] = fma(qk[i], a, acc[0]);
-                if (qm) w[i] = fma(-bprev, qm[i], a);
+                if (qm) w[i] = fma(-*bprev_p, qm[i], a);
             }, slot1(SC_LANCZOS));
             return 0;
         };
@@ -2814,23 +2964,31 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
         }, slot1(SC_LANCZOS + 2));
         CHECK_LAUNCH(ctx);
         TRY(fetch_scalars(ctx, SC_LANCZOS + 2, 1));
-        total += ctx->hsc[SC_LANCZOS + 2];
+        if (cone_lead(ctx)) total += ctx->hsc[SC_LANCZOS + 2];
     }
     for (auto &c : ctx->cones) {
+        if (!cone_mine(ctx, c)) continue; /* by cone: the owner runs the cone's Lanczos, the sum is all-reduced below */
         /* slack S = C - sum lambda_i A_i on the pattern */
         run_wsum(ctx, c, ctx->lam, true, true, -1.0, c.S);
         const int32_t *fp = c.f_ptr, *fc = c.f_col, *fs = c.f_slot;
         const double *Sv = c.S;
         const int64_t n = c.n;
         double theta = 0.0;
-        auto apply = [&](const double *qk, const double *qm, double bprev, double *w) -> int {
+        auto apply = [&](const double *qk, const double *qm, const double *bprev_p, double *w) -> int {
             Prof pr(ctx, KC_SPMM);
             k_lanczos_symv<<<grid_for(ctx, n * 32, (const void *)k_lanczos_symv), LGPU_TPB, 0, ctx->stream>>>(
-                n, fp, fc, fs, Sv, qk, qm, bprev, w, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_LANCZOS));
+                n, fp, fc, fs, Sv, qk, qm, bprev_p, w, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_LANCZOS));
             return 0;
         };
         TRY(lanczos_min_eig(ctx, n, n, apply, &theta));
         total += fabs(std::min(theta, 0.0));
+    }
+    if (ctx->cone_par) {
+        ctx->hsc[SC_TMP] = total;
+        CU(ctx, cudaMemcpyAsync(ctx->dsc + SC_TMP, ctx->hsc + SC_TMP, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(allreduce_scalars(ctx, SC_TMP, 1));
+        TRY(fetch_scalars(ctx, SC_TMP, 1));
+        total = ctx->hsc[SC_TMP];
     }
     *sum_neg_eig = total;
     return 0;

@@ -187,6 +187,10 @@ struct lgpu_ctx {
     /* row-block partition over `world` ranks (NCCL); world == 1: single GPU */
     int rank = 0, world = 1;
     void *comm = nullptr;     /* ncclComm_t */
+    /* by-cone partition (world > 1 and the problem is not the single MaxCut-type cone): everything replicated, the operator
+     * work of cone c done by rank cone_owner[c] (lgpu_api.cu, "by-cone partition") */
+    bool cone_par = false;
+    std::vector<int> cone_owner;
     double *gfull = nullptr;  /* all-gather mode: [world * n_alloc * ld] factor rows of every rank, global row order */
     /* halo mode: only the remote rows this rank's CSR rows reference are exchanged (ncclSend/ncclRecv), into
      * `halo` (rows grouped by owner, ascending); CSR columns are remapped: local row j - lo, halo row n_alloc + k */
@@ -210,6 +214,10 @@ struct lgpu_ctx {
     unsigned long long xseq = 0, aseq = 0;        /* exchange / all-reduce sequence numbers (same on all ranks) */
     const double *halo_cur = nullptr;             /* halo buffer the current product reads */
     unsigned int *put_counter = nullptr;
+    bool fuse_put = true;                         /* LORADS_FUSE_PUT=0: separate k_put_rows after the direction pass (A/B) */
+    int32_t *put_dest = nullptr;                  /* [n_loc * (world - 1)] row of each own row in each peer's halo, or -1 */
+    const double *pending_put_x = nullptr;        /* vector whose halo rows the direction pass already PUT ... */
+    unsigned long long pending_put_seq = 0;       /* ... under this exchange sequence number */
     /* fused MaxCut-type path (single diag_only cone, no LP): CR = C R carried across iterations, CD = C D */
     bool dense_dmma = true;   /* dense-aggregate cones: SYR2K / SYMM on the FP64 tensor pipe */
     bool fast_enabled = true;

@@ -61,7 +61,9 @@ struct NoPost {
 
 /* `post(dsc)` runs once, in the finishing thread, after the slots are written: derived scalars (an L-BFGS alpha,
  * 1/<y,s>, ...) are produced without a separate one-thread launch. */
-template <int K, class P = NoPost>
+/* SYS: the CTA's earlier stores include stores to PEER memory (NVLink) that `post` is about to publish with a flag:
+ * the fence ahead of the arrival counter is then system-wide. */
+template <int K, class P = NoPost, bool SYS = false>
 __device__ __forceinline__ void grid_reduce_finish(double (&v)[K], double *partials, unsigned int *counter,
                                                    double *dsc, const SlotSpec<K> &spec, P post = P())
 {
@@ -81,7 +83,8 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[K], double *parti
             for (int w = 0; w < LGPU_TPB / 32; ++w) t += sh[k][w];
             partials[(size_t)k * gridDim.x + blockIdx.x] = t;
         }
-        __threadfence();
+        if (SYS) __threadfence_system();
+        else __threadfence();
         unsigned int done = atomicAdd(counter, 1u);
         is_last = (done == gridDim.x - 1);
     }
@@ -1060,7 +1063,26 @@ struct DirCoef {
     double a1, a0, w0, w1;
     int nn;
 };
-template <int G>
+/* PUT (partitioned runs, peer memory): the row of D just formed is also stored into the halo buffer of every peer whose
+ * CSR rows reference it -- dest[i * npeer + j] is its row there (or -1) -- so the halo exchange rides inside the
+ * direction pass: no pack kernel, no second read of D, and the NVLink stores overlap the pass's own HBM streams.  The
+ * finishing thread publishes the exchange's sequence number in every peer's block (fused compute + transfer over
+ * peer-mapped memory; the consumers wait in k_wait_sources). */
+struct PeerDirect {
+    int npeer;                                /* world - 1 */
+    double *dst[LGPU_MAX_WORLD];              /* [j] halo base of the j-th peer (this exchange's buffer) */
+    unsigned long long *flag[LGPU_MAX_WORLD]; /* [j] &peer_blk->xflag[my rank] */
+    unsigned long long seq;
+};
+struct PublishSeq { /* runs in the finishing thread of the grid, after every CTA's system-wide fence */
+    PeerDirect pd;
+    __device__ void operator()(double *) const
+    {
+        __threadfence_system();
+        for (int j = 0; j < pd.npeer; ++j) st_release_sys_u64(pd.flag[j], pd.seq);
+    }
+};
+template <int G, bool PUT>
 __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirCoef cf, const double *__restrict__ Gd,
                                                          const double *__restrict__ s1, const double *__restrict__ y1,
                                                          const double *__restrict__ s0, const double *__restrict__ y0,
@@ -1068,7 +1090,8 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
                                                          double *__restrict__ D, const int32_t *__restrict__ rcptr,
                                                          const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
                                                          double *__restrict__ q1, double *__restrict__ q2, double *partials,
-                                                         unsigned int *counter, double *dsc, SlotSpec<1> spec)
+                                                         unsigned int *counter, double *dsc, SlotSpec<1> spec,
+                                                         const int32_t *__restrict__ dest, PeerDirect pd)
 {
     const int lane = threadIdx.x % G;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -1098,6 +1121,12 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
                 }
                 const double2 d = make_double2(-q.x, -q.y);
                 reinterpret_cast<double2 *>(D)[w] = d;
+                if (PUT) {
+                    for (int j = 0; j < pd.npeer; ++j) {
+                        const int slot = dest[(size_t)i * pd.npeer + j];
+                        if (slot >= 0) reinterpret_cast<double2 *>(pd.dst[j])[(size_t)slot * ld2 + c] = d;
+                    }
+                }
                 const double2 r = reinterpret_cast<const double2 *>(Rm)[w];
                 const double2 cr = reinterpret_cast<const double2 *>(CR)[w];
                 rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
@@ -1113,7 +1142,12 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
                 q2[rcgid[t]] = a * dd;
             }
     }
-    grid_reduce_finish<1>(red, partials, counter, dsc, spec);
+    if (PUT) {
+        __threadfence_system(); /* every thread's peer stores are performed before its CTA reports in */
+        grid_reduce_finish<1, PublishSeq, true>(red, partials, counter, dsc, spec, PublishSeq{pd});
+    } else {
+        grid_reduce_finish<1>(red, partials, counter, dsc, spec);
+    }
 }
 
 /* One fused streaming pass for everything that follows the line search (tau known):

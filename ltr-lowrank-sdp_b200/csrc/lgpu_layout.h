@@ -557,15 +557,14 @@ static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int
         }
     }
     lap("fused arrays");
-    L.partitioned = world > 1;
+    L.partitioned = false;
     if (world <= 1) return 0;
     /* row-block partition: this rank keeps the CSR rows, the row -> constraint lists and the vector rows of
      * [lo, hi); column indices and constraint ids stay global (they index the all-gathered factor and the
-     * replicated-length m-vectors).  Only the fused MaxCut-type layout is partitioned in this build. */
-    if (!(diag_only && mA == m && single_cone_no_lp)) {
-        err = "row-block partitioned runs need one SDP block with single-diagonal-entry constraints (MaxCut-type)";
-        return 1;
-    }
+     * replicated-length m-vectors).  Only the fused MaxCut-type layout is partitioned by rows; every other problem
+     * (several cones, an LP block, general constraints) keeps whole cones and is partitioned BY CONE (lgpu_api.cu). */
+    if (!(diag_only && mA == m && single_cone_no_lp)) return 0;
+    L.partitioned = true;
     int64_t lo, hi, rpr;
     lgpu_partition_rows(n, world, rank, &lo, &hi, &rpr);
     L.lo = lo; L.hi = hi; L.rows_per_rank = rpr;

@@ -36,6 +36,19 @@ def test_partitioned_run_matches_single_gpu(built, world, graph, halo, peer):
     assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_by_cone_partition_vs_reference_goldens(built, world):
+    """multi-block / LP / general-cone problems on several GPUs (partition by cone, m-vector all-reduce) against the
+    reference-generated golden vectors, through the same sequence and tolerances as the single-GPU parity test"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(29760 + world), os.path.join(ROOT, "tests", "_multi_gpu_cone_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ))
+    assert out.returncode == 0 and "BY_CONE_OK" in out.stdout, out.stdout[-4000:] + out.stderr[-3000:]
+
+
 @pytest.mark.parametrize("graph", ["torus", "random"])
 def test_binary_partitioned_run(built, tmp_path, graph):
     """the drop-in binary with --ranks 2 (forks one process per GPU, NCCL id over pipes) against the same binary on one

@@ -24,10 +24,15 @@ def lb(built):
     return built
 
 
+# tests/_multi_gpu_cone_worker.py runs the sequence test below on several GPUs: it plants a factory that returns a context
+# already joined to the ranks' communicator
+CTX_FACTORY = [None]
+
+
 def _problem(lb, name):
     g = golden(name)
     p = lb.read_sdpa(inst_path(name))
-    ctx = lb.Context(0).load(p)
+    ctx = (CTX_FACTORY[0]() if CTX_FACTORY[0] else lb.Context(0)).load(p)
     q = orc.read_sdpa(inst_path(name))
     cones = [orc.build_cone(bk, q.m) for bk in q.blocks]
     return g, p, ctx, q, cones

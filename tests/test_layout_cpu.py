@@ -216,11 +216,18 @@ def test_layout_does_not_depend_on_thread_count(built, monkeypatch):
                 assert np.array_equal(got[nm], ref[nm]), (nm, thr)
 
 
-def test_partitioned_layout_rejects_general_cones(built):
+def test_general_cones_are_not_row_sliced(built):
+    """only the single MaxCut-type cone is partitioned by rows; any other cone keeps its whole layout on every rank (the
+    solver then partitions BY CONE): with world = 2 the arrays equal the one-GPU ones and no row-block slice exists"""
     rng = np.random.default_rng(2)
     p = _random_problem(built, rng, n=60, m=40, per_con=3, nobj=50, shuffle=False)
-    with pytest.raises(built.LoradsError):
-        built.cone_layout(p, 0, ["f_ptr"], world=2, rank=0)
+    names = ["f_ptr", "f_col", "f_slot", "a_ptr", "a_slot", "t_ptr", "pat_row", "pat_col", "lf_ptr", "send_idx"]
+    one = built.cone_layout(p, 0, names, world=1, rank=0)
+    for r in range(2):
+        two = built.cone_layout(p, 0, names, world=2, rank=r)
+        for nm in names:
+            assert np.array_equal(one[nm], two[nm]), nm
+        assert len(two["lf_ptr"]) == 0 and len(two["send_idx"]) == 0
 
 
 @pytest.mark.parametrize("graph,world", [("torus", 2), ("torus", 4), ("random", 3), ("random", 8)])
