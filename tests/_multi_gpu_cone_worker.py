@@ -19,7 +19,7 @@ import lorads_b200 as lb  # noqa: E402
 import pytest  # noqa: E402
 import test_gpu_parity as T  # noqa: E402
 
-FIXTURES = ["multiblock_sdp", "multiblock_lp", "general_sparse_n60", "theta_n30", "dense_constraint_n24"]
+FIXTURES = ["multiblock_sdp", "multiblock_lp", "control_like_12_6", "general_sparse_n60", "theta_n30", "dense_constraint_n24"]
 
 
 def main():

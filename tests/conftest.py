@@ -16,7 +16,7 @@ for p in (PKG, ORACLE):
         sys.path.insert(0, p)
 
 FIXTURES = ["G11", "maxcut_torus_8x10", "maxcut_torus_20x30", "general_sparse_n60", "theta_n30",
-            "dense_constraint_n24", "multiblock_sdp", "multiblock_lp"]
+            "dense_constraint_n24", "multiblock_sdp", "multiblock_lp", "control_like_12_6"]
 
 
 def pytest_configure(config):

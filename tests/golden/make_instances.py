@@ -211,6 +211,34 @@ def gen_multiblock(path, dims, nlp, m, seed, lp=True):
     write_sdpa(path, m, d, b, ent)
 
 
+def gen_control_like(path, dims, m, seed):
+    """SDPLIB `control`-type stand-in (BASELINE configs[1]): two small dense blocks [2k, k] in which EVERY constraint
+    couples both blocks through dense-ish symmetric pieces (an LMI in SDPA form), so both cones are dense containers
+    (every A_i non-zero in each block) with dense aggregates (n < 20 / nnzP >= 0.1 tri); b from a feasible X0."""
+    rng = np.random.default_rng(seed)
+    ent, X0 = [], []
+    for n in dims:
+        Z = rng.normal(size=(n, 3))
+        X0.append(Z @ Z.T + 0.1 * np.eye(n))
+    for k, n in enumerate(dims):
+        for i in range(n):
+            ent.append((0, k + 1, i + 1, i + 1, -(1.0 + float(rng.random()))))
+            for j in range(i + 1, n):
+                if rng.random() < 0.3:
+                    ent.append((0, k + 1, i + 1, j + 1, 0.2 * float(rng.normal())))
+    b = np.zeros(m)
+    for q in range(m):
+        for k, n in enumerate(dims):
+            dens = 0.6 if q % 3 else 0.25
+            for i in range(n):
+                for j in range(i, n):
+                    if rng.random() < dens or (i == j == q % n):
+                        v = 0.25 * float(rng.normal())
+                        ent.append((q + 1, k + 1, i + 1, j + 1, v))
+                        b[q] += v * X0[k][i, j] * (1.0 if i == j else 2.0)
+    write_sdpa(path, m, dims, b, ent)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_maxcut_torus(os.path.join(OUT, "maxcut_torus_8x10.dat-s"), 8, 10, 11)
@@ -220,6 +248,7 @@ def main():
     gen_dense_constraint(os.path.join(OUT, "dense_constraint_n24.dat-s"), 24, 12, 9)
     gen_multiblock(os.path.join(OUT, "multiblock_sdp.dat-s"), [25, 30, 22, 28], 0, 40, 13, lp=False)
     gen_multiblock(os.path.join(OUT, "multiblock_lp.dat-s"), [25, 30, 22, 28], 12, 40, 17, lp=True)
+    gen_control_like(os.path.join(OUT, "control_like_12_6.dat-s"), [12, 6], 21, 23)
     if os.path.exists("/root/reference/hallar/py/graphs/G1.mtx"):
         print("G1:", gen_g1(os.path.join(OUT, "G1.dat-s")))
     print("wrote", sorted(os.listdir(OUT)))

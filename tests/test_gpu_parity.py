@@ -210,11 +210,22 @@ def test_alm_admm_sequence_vs_reference(lb, name, mode):
         w = np.linalg.eigvalsh(ctx.gram(2, c))
         tot += int(np.sum(w > 1e-6 * w[-1])) if w[-1] > 0 else 0
     assert tot == int(g["oracle_rank_admm"])
-    # rank augmentation (AUG_RANK, lorads_solver.c:1154-1254)
+    # rank augmentation (AUG_RANK, lorads_solver.c:1154-1254): against the reference's result at the accuracy of the ADMM
+    # iterate it was applied to, and EXACTLY as an operation -- old columns copied bit for bit, new column r_old + j holds
+    # 1 / sqrt(dr) at row j and zeros elsewhere, for R, U, V and Grad alike
+    before = {(w, c): ctx.get_factor(w, c) for w in (lb.R, lb.U, lb.V, lb.GRAD) for c in range(nc)}
     ctx.aug_rank([int(r) for r in g["rank_aug"]])
     for c in range(nc):
         assert rel(ctx.get_factor(lb.R, c), g[f"Raug_{c}"]) < 1e-6
         assert ctx.get_factor(lb.R, c).shape[1] == int(g["rank_aug"][c])
+        for w in (lb.R, lb.U, lb.V, lb.GRAD):
+            old, new = before[(w, c)], ctx.get_factor(w, c)
+            r_old, dr = old.shape[1], new.shape[1] - old.shape[1]
+            assert np.array_equal(new[:, :r_old], old)
+            seed = np.zeros((old.shape[0], dr))
+            k = min(old.shape[0], dr)
+            seed[np.arange(k), np.arange(k)] = 1.0 / np.sqrt(k)
+            assert np.array_equal(new[:, r_old:], seed)
     ctx.close()
 
 

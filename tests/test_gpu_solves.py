@@ -28,6 +28,8 @@ CASES = {
     "G1": (os.path.join(INST, "G1.dat-s"), GSET + ["--reoptLevel", "0"], True),
     "G11": (os.path.join(INST, "G11.dat-s"), GSET, True),
     "torus_100x200": (None, GSET + ["--reoptLevel", "0"], False),
+    "control_like_12_6": (os.path.join(INST, "control_like_12_6.dat-s"), [], True),   # configs[1] stand-in: two coupled dense blocks
+    "multiblock_sdp": (os.path.join(INST, "multiblock_sdp.dat-s"), [], False),
     "MC_500": (os.path.join(DATA, "MC_500.dat-s"), [], True),
     "checker_1.5": (os.path.join(DATA, "checker_1.5.dat-s"), [], False),
     "ice_2.0": (os.path.join(DATA, "ice_2.0.dat-s"), [], False),
