@@ -610,6 +610,28 @@ def maxcut_problem(n: int, ei: np.ndarray, ej: np.ndarray, w: np.ndarray) -> Sdp
     return SdpaProblem(n, [n], np.ones(n), [beg], [mat_idx], [mat_elem])
 
 
+def block_maxcut_problem(blocks: Sequence[tuple]) -> SdpaProblem:
+    """A multi-block SDP: block k is the MaxCut SDP of graph k = (n, ei, ej, w); constraint ids run block after block
+    (m = sum n_k) and each touches its own block only.  With more than one block the solver takes the general (per-cone)
+    path, and on several GPUs the by-cone partition."""
+    singles = [maxcut_problem(*b) for b in blocks]
+    m = sum(q.m for q in singles)
+    beg, idx, val, off = [], [], [], 0
+    for q in singles:
+        qb = q.mat_beg[0]
+        nobj = int(qb[1])
+        full = np.empty(m + 2, dtype=np.int64)
+        full[0], full[1] = 0, nobj
+        full[2:2 + off] = nobj                                  # constraints of earlier blocks: empty here
+        full[1 + off:1 + off + q.m + 1] = qb[1:]                # this block's constraints
+        full[1 + off + q.m + 1:] = qb[-1]                       # constraints of later blocks: empty here
+        beg.append(full)
+        idx.append(q.mat_idx[0])
+        val.append(q.mat_elem[0])
+        off += q.m
+    return SdpaProblem(m, [int(q.dims[0]) for q in singles], np.ones(m), beg, idx, val)
+
+
 def torus_graph(rows: int, cols: int, seed: int, pm1: bool = True):
     """rows x cols toroidal grid (G81-like when 100 x 200 with +-1 weights)."""
     r, c = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")

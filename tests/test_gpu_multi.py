@@ -49,6 +49,41 @@ def test_by_cone_partition_vs_reference_goldens(built, world):
     assert out.returncode == 0 and "BY_CONE_OK" in out.stdout, out.stdout[-4000:] + out.stderr[-3000:]
 
 
+def test_binary_by_cone_run(built, tmp_path):
+    """the drop-in binary with --ranks 2 on problems that are NOT the single MaxCut-type cone (two coupled dense blocks;
+    three MaxCut blocks): the by-cone partition must reproduce the one-GPU solve -- same status, same iteration counts
+    within north-star's 5 %, objective to 1e-6"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    lb = built
+    blk = tmp_path / "three_blocks.dat-s"
+    lb.write_sdpa(str(blk), lb.block_maxcut_problem([(60 * 50,) + lb.torus_graph(60, 50, s) for s in (1, 2, 3)]))
+    cases = [(os.path.join(ROOT, "tests", "golden", "instances", "control_like_12_6.dat-s"), []),
+             (str(blk), ["--phase1Tol", "1e-2", "--heuristicFactor", "10", "--reoptLevel", "0"])]
+    for inst, flags in cases:
+        res = {}
+        for ranks in (1, 2):
+            out = lb.run_solver([inst] + flags + ["--timeSecLimit", "300"] + (["--ranks", "2"] if ranks == 2 else []), timeout=900)
+            assert out.returncode == 0, out.stderr[-2000:]
+            inner = admm = obj = status = None
+            for line in out.stdout.splitlines():
+                if "OuterIter:" in line and "InnerIter:" in line:
+                    inner = int(line.split("InnerIter:")[1].split()[0])
+                elif line.startswith("ADMM Iter:"):
+                    admm = int(line.split("Iter:")[1].split()[0]) + 1
+                elif "1.Primal Objective:" in line:
+                    obj = float(line.split(":")[-1])
+                elif line.startswith("End Program"):
+                    status = line.strip()
+            res[ranks] = (inner, admm, obj, status)
+        a, b = res[2], res[1]
+        print(inst, "ranks 2:", a, "ranks 1:", b)
+        assert a[3] == b[3]
+        assert abs(a[0] - b[0]) <= max(3, 0.05 * b[0]), (a, b)
+        assert abs(a[2] - b[2]) <= 1e-6 * max(abs(b[2]), 1.0), (a, b)
+
+
 @pytest.mark.parametrize("graph", ["torus", "random"])
 def test_binary_partitioned_run(built, tmp_path, graph):
     """the drop-in binary with --ranks 2 (forks one process per GPU, NCCL id over pipes) against the same binary on one
