@@ -94,6 +94,14 @@ int lgpu_cone_layout_build(lgpu_layout **out, int64_t n, int64_t m, const int64_
 int lgpu_cone_layout_get(const lgpu_layout *layout, const char *name, int64_t cap_bytes, void *out, int64_t *count,
                          int *elem_bytes);
 void lgpu_cone_layout_free(lgpu_layout *layout);
+/* Row relabelling for gather locality: when the fused MaxCut-type layout is used and a breadth-first relabelling of the
+ * graph of C brings the entries of the symmetric CSR near the diagonal (the factor rows a row gathers then sit in L2, the
+ * halos of a row-block partition become thin), the library stores the factors in that order.  Nothing changes at this
+ * interface: factors are passed in and returned in the caller's row order.  out = {applied, share of CSR entries within
+ * +-65536 rows of the diagonal before, after}.  LORADS_REORDER=0/1 forbids / forces it.  The reference has no counterpart
+ * (it walks its entries in file order, lorads_sdp_data.c:750-763). */
+int lgpu_cone_reorder_info(const lgpu_ctx *ctx, int cone, double out[3]);
+
 /* aggregated lower pattern of a cone in the reference's order (sorted by (col,row)) */
 int lgpu_cone_pattern(const lgpu_ctx *ctx, int cone, int64_t cap, int32_t *row, int32_t *col);
 /* cal_sdp_const (lorads_solver.c:1457-1485): out = {|C|_1, |C|_2, |C|_inf, |b|_1, |b|_2, |b|_inf(Q2 quirk)} */

@@ -700,6 +700,7 @@ extern "C" const char *lgpu_profile_class_name(int cls)
 
 static void free_cone(DevCone &c)
 {
+    dev_free(c.perm); dev_free(c.iperm); c.reordered = false; c.h_iperm.clear();
     dev_free(c.pat_row); dev_free(c.pat_col); dev_free(c.cval); dev_free(c.c_slot); dev_free(c.c_coef);
     dev_free(c.a_ptr); dev_free(c.a_slot); dev_free(c.a_coef); dev_free(c.con_gid); dev_free(c.long_con); c.n_long_con = 0;
     dev_free(c.t_ptr); dev_free(c.t_loc); dev_free(c.t_gid); dev_free(c.t_val);
@@ -974,6 +975,14 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     c.c_nrminf = L.c_nrminf;
     c.h_pat_row.swap(L.pat_row);
     c.h_pat_col.swap(L.pat_col);
+    c.reordered = L.reordered;
+    c.window_before = L.window_hits_before;
+    c.window_after = L.window_hits_after;
+    if (L.reordered) {
+        TRY(dev_upload(ctx, &c.perm, L.perm));
+        TRY(dev_upload(ctx, &c.iperm, L.iperm));
+        c.h_iperm = L.iperm;
+    }
     c.n = n;
     c.n_glob = n;
     c.row_lo = 0;
@@ -1021,8 +1030,8 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
         return 0;
     }
     const int64_t mA = L.mA, nnzP = L.nnzP;
-    TRY(dev_upload(ctx, &c.pat_row, c.h_pat_row));
-    TRY(dev_upload(ctx, &c.pat_col, c.h_pat_col));
+    TRY(dev_upload(ctx, &c.pat_row, L.reordered ? L.dev_pat_row : c.h_pat_row));
+    TRY(dev_upload(ctx, &c.pat_col, L.reordered ? L.dev_pat_col : c.h_pat_col));
     TRY(dev_upload(ctx, &c.cval, L.cval));
     TRY(dev_upload(ctx, &c.c_slot, L.c_slot));
     TRY(dev_upload(ctx, &c.c_coef, L.c_coef));
@@ -1142,6 +1151,17 @@ extern "C" int lgpu_cone_info(const lgpu_ctx *ctx, int cone, int64_t out[6])
     return 0;
 }
 
+/* row relabelling for gather locality (lgpu_layout.h bfs_relabel): out = {applied (0/1), share of the CSR entries within
+ * +-65536 rows of the diagonal before, after}; invisible at the ABI (factors go in and out in the caller's row order) */
+extern "C" int lgpu_cone_reorder_info(const lgpu_ctx *ctx, int cone, double out[3])
+{
+    if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
+    const DevCone &c = ctx->cones[cone];
+    out[0] = c.reordered ? 1.0 : 0.0;
+    out[1] = c.window_before;
+    out[2] = c.window_after;
+    return 0;
+}
 extern "C" int lgpu_cone_pattern(const lgpu_ctx *ctx, int cone, int64_t cap, int32_t *row, int32_t *col)
 {
     if (!ctx || cone < 0 || cone >= ctx->ncones) return 1;
@@ -1355,23 +1375,34 @@ static double *mvec_of(lgpu_ctx *ctx, int which)
 /* host column-major n x r -> device row-major n x ld at dst */
 /* host column-major n_glob x r -> device row-major rows [row_lo, row_lo + n) x ld at dst.  Only the owned rows cross
  * the bus (a strided 2-D copy: r column pieces of n doubles). */
+/* pc: the cone whose row relabelling (if any) applies; nullptr = none */
 static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *cm, double *dst, int64_t n_glob = -1,
-                         int64_t row_lo = 0)
+                         int64_t row_lo = 0, const DevCone *pc = nullptr)
 {
     if (n_glob < 0) n_glob = n;
     if (n <= 0) return 0;
-    const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
-    /* straight from the caller's buffer: a pinned buffer goes by DMA, a pageable one is staged by the runtime */
-    TRY(ensure_dstage(ctx, bytes));
-    if (n_glob == n)
-        CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    else
-        CU(ctx, cudaMemcpy2DAsync(ctx->dstage, sizeof(double) * (size_t)n, cm + row_lo, sizeof(double) * (size_t)n_glob,
-                                  sizeof(double) * (size_t)n, (size_t)r, cudaMemcpyHostToDevice, ctx->stream));
+    const bool relabel = pc != nullptr && pc->reordered;
     dim3 blk(32, 8);
-    {
+    if (relabel && n_glob != n) {
+        /* partitioned + relabelled: this rank's device rows are scattered rows of the caller's factor: stage it whole */
+        const size_t bytes = sizeof(double) * (size_t)n_glob * (size_t)r;
+        TRY(ensure_dstage(ctx, bytes));
+        CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
         Prof pr(ctx, KC_LAYOUT);
-        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, n, 0, dst);
+        k_gather_rows_cm<<<grid_for(ctx, n * ld), LGPU_TPB, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, n_glob,
+                                                                              pc->iperm + row_lo, dst);
+    } else {
+        const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
+        /* straight from the caller's buffer: a pinned buffer goes by DMA, a pageable one is staged by the runtime */
+        TRY(ensure_dstage(ctx, bytes));
+        if (n_glob == n)
+            CU(ctx, cudaMemcpyAsync(ctx->dstage, cm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            CU(ctx, cudaMemcpy2DAsync(ctx->dstage, sizeof(double) * (size_t)n, cm + row_lo, sizeof(double) * (size_t)n_glob,
+                                      sizeof(double) * (size_t)n, (size_t)r, cudaMemcpyHostToDevice, ctx->stream));
+        Prof pr(ctx, KC_LAYOUT);
+        k_col2row<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, (const double *)ctx->dstage, n, 0, dst,
+                                                                      relabel ? pc->perm : nullptr);
     }
     CHECK_LAUNCH(ctx);
     CU(ctx, cudaStreamSynchronize(ctx->stream)); /* the caller may reuse its buffer as soon as this returns */
@@ -1380,23 +1411,34 @@ static int upload_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const 
 /* the reverse.  In a partitioned run each rank writes ONLY the rows it owns into the caller's n_glob x r array (the
  * other rows are left untouched); the caller assembles the ranks' pieces if it needs the whole factor. */
 static int download_factor(lgpu_ctx *ctx, int64_t n, int64_t r, int64_t ld, const double *src, double *cm, int64_t n_glob = -1,
-                           int64_t row_lo = 0)
+                           int64_t row_lo = 0, const DevCone *pc = nullptr)
 {
     if (n_glob < 0) n_glob = n;
     if (n <= 0) return 0;
+    const bool relabel = pc != nullptr && pc->reordered;
     const size_t bytes = sizeof(double) * (size_t)n * (size_t)r;
     TRY(ensure_dstage(ctx, bytes));
     dim3 blk(32, 8);
     {
         Prof pr(ctx, KC_LAYOUT);
-        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage, n, 0);
+        k_row2col<<<(unsigned)((n + 31) / 32), blk, 0, ctx->stream>>>(n, (int)r, (int)ld, src, (double *)ctx->dstage, n, 0,
+                                                                      (relabel && n_glob == n) ? pc->perm : nullptr);
     }
     CHECK_LAUNCH(ctx);
-    if (n_glob == n)
+    if (n_glob == n) {
         CU(ctx, cudaMemcpyAsync(cm, ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    else
+    } else if (!relabel) {
         CU(ctx, cudaMemcpy2DAsync(cm + row_lo, sizeof(double) * (size_t)n_glob, ctx->dstage, sizeof(double) * (size_t)n,
                                   sizeof(double) * (size_t)n, (size_t)r, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        /* partitioned + relabelled: the owned device rows are scattered rows of the caller's array */
+        std::vector<double> tmp((size_t)n * (size_t)r);
+        CU(ctx, cudaMemcpyAsync(tmp.data(), ctx->dstage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t col = 0; col < r; ++col)
+            for (int64_t t = 0; t < n; ++t) cm[(size_t)col * n_glob + pc->h_iperm[row_lo + t]] = tmp[(size_t)col * n + t];
+        return 0;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -1408,14 +1450,14 @@ extern "C" int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double 
     DevCone &c = ctx->cones[cone];
     if (which == LGPU_R) ctx->cr_valid = false;
     if (which == LGPU_U) { ctx->cd_valid = false; ctx->epi_done = false; }
-    return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off, c.n_glob, c.row_lo);
+    return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off, c.n_glob, c.row_lo, &c);
 }
 extern "C" int lgpu_get_factor(lgpu_ctx *ctx, int which, int cone, double *cm)
 {
     if (!ctx || !ctx->vars_ready || cone < 0 || cone >= ctx->ncones || !flat_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     DevCone &c = ctx->cones[cone];
-    return download_factor(ctx, c.n, c.r, c.ld, flat_of(ctx, which) + c.off, cm, c.n_glob, c.row_lo);
+    return download_factor(ctx, c.n, c.r, c.ld, flat_of(ctx, which) + c.off, cm, c.n_glob, c.row_lo, &c);
 }
 extern "C" int lgpu_set_lp(lgpu_ctx *ctx, int which, const double *v)
 {
@@ -1523,7 +1565,8 @@ extern "C" int lgpu_aug_rank(lgpu_ctx *ctx, const int64_t *new_rank)
             DevCone &cn = ctx->cones[c];
             Prof pr(ctx, KC_LAYOUT);
             k_restride_aug<<<grid_for(ctx, cn.n * cn.ld), LGPU_TPB, 0, ctx->stream>>>(
-                cn.n, (int)o_r[c], (int)o_ld[c], (int)cn.r, (int)cn.ld, olds[w] + o_off[c], news[w] + cn.off, 1, cn.n_glob, cn.row_lo);
+                cn.n, (int)o_r[c], (int)o_ld[c], (int)cn.r, (int)cn.ld, olds[w] + o_off[c], news[w] + cn.off, 1, cn.n_glob, cn.row_lo,
+                cn.reordered ? cn.iperm : nullptr);
         }
         if (ctx->lp.n > 0)
             CU(ctx, cudaMemcpyAsync(news[w] + ctx->lp.off, olds[w] + o_lp_off, sizeof(double) * ctx->lp.n,
@@ -3009,10 +3052,10 @@ static int op_stage_factors(lgpu_ctx *ctx, DevCone &c, int64_t r, const double *
     t->ld = (r + 3) & ~(int64_t)3;
     const size_t sz = (size_t)c.n * t->ld;
     CU(ctx, cudaMalloc((void **)&t->U, sizeof(double) * sz));
-    TRY(upload_factor(ctx, c.n, r, t->ld, U, t->U));
+    TRY(upload_factor(ctx, c.n, r, t->ld, U, t->U, -1, 0, &c));
     if (V != nullptr && V != U) {
         CU(ctx, cudaMalloc((void **)&t->V, sizeof(double) * sz));
-        TRY(upload_factor(ctx, c.n, r, t->ld, V, t->V));
+        TRY(upload_factor(ctx, c.n, r, t->ld, V, t->V, -1, 0, &c));
     } else {
         t->V = t->U;
     }
@@ -3103,7 +3146,7 @@ extern "C" int lgpu_op_wsum_mulrk(lgpu_ctx *ctx, int cone, int64_t r, const doub
         run_spmm(ctx, c, t.ld, c.S, t.U, 1.0, 0.0, nullptr, t.Y);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; }
-        if (!rc) rc = download_factor(ctx, c.n, r, t.ld, t.Y, Y);
+        if (!rc) rc = download_factor(ctx, c.n, r, t.ld, t.Y, Y, -1, 0, &c);
     }
     op_free(&t);
     return rc;

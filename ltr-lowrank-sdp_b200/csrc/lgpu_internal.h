@@ -118,6 +118,11 @@ struct DevCone {
     double c_nrm1 = 0, c_nrm2sq = 0, c_nrminf = 0;
     /* host copies kept for lgpu_cone_pattern */
     std::vector<int32_t> h_pat_row, h_pat_col;
+    /* row relabelling for gather locality (fused layout): device row perm[i] = caller's row i; iperm = the inverse */
+    bool reordered = false;
+    double window_before = 0.0, window_after = 0.0;
+    int32_t *perm = nullptr, *iperm = nullptr;
+    std::vector<int32_t> h_iperm;
     /* device arrays */
     int32_t *pat_row = nullptr, *pat_col = nullptr;
     double *cval = nullptr;                      /* [nnzP] C on the pattern */

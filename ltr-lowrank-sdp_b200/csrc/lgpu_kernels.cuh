@@ -476,8 +476,10 @@ __global__ void __launch_bounds__(LGPU_TPB) k_spmm(int64_t n, const int32_t *__r
 
 /* host column-major (cm_ld rows, this rank's rows start at cm_row0)  <->  device row-major n x ld (padding columns
  * zeroed) */
+/* perm != nullptr (row relabelling for gather locality, lgpu_layout.h): the caller's row `row` lives in device row perm[row] */
 __global__ void __launch_bounds__(LGPU_TPB) k_col2row(int64_t n, int r, int ld, const double *__restrict__ cm,
-                                                      int64_t cm_ld, int64_t cm_row0, double *__restrict__ rm)
+                                                      int64_t cm_ld, int64_t cm_row0, double *__restrict__ rm,
+                                                      const int32_t *__restrict__ perm)
 {
     __shared__ double tile[32][33];
     const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -492,14 +494,15 @@ __global__ void __launch_bounds__(LGPU_TPB) k_col2row(int64_t n, int r, int ld, 
         for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
             const int64_t row = row0 + rr;
             const int col = c0 + threadIdx.x;
-            if (row < n && col < ld) rm[(size_t)row * ld + col] = tile[threadIdx.x][rr];
+            if (row < n && col < ld) rm[(size_t)(perm ? perm[row] : row) * ld + col] = tile[threadIdx.x][rr];
         }
         __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, const double *__restrict__ rm,
-                                                      double *__restrict__ cm, int64_t cm_ld, int64_t cm_row0)
+                                                      double *__restrict__ cm, int64_t cm_ld, int64_t cm_row0,
+                                                      const int32_t *__restrict__ perm)
 {
     __shared__ double tile[32][33];
     const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, 
         for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
             const int64_t row = row0 + rr;
             const int col = c0 + threadIdx.x;
-            tile[rr][threadIdx.x] = (row < n && col < r) ? rm[(size_t)row * ld + col] : 0.0;
+            tile[rr][threadIdx.x] = (row < n && col < r) ? rm[(size_t)(perm ? perm[row] : row) * ld + col] : 0.0;
         }
         __syncthreads();
         for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
@@ -519,11 +522,25 @@ __global__ void __launch_bounds__(LGPU_TPB) k_row2col(int64_t n, int r, int ld, 
     }
 }
 
+/* partitioned run with relabelled rows: device row t of this rank is the caller's row src[t] of the whole column-major factor */
+__global__ void __launch_bounds__(LGPU_TPB) k_gather_rows_cm(int64_t nloc, int r, int ld, const double *__restrict__ cm,
+                                                             int64_t cm_ld, const int32_t *__restrict__ src, double *__restrict__ rm)
+{
+    const int64_t total = nloc * (int64_t)ld;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t t = i / ld;
+        const int col = (int)(i - t * ld);
+        rm[i] = col < r ? cm[(size_t)col * cm_ld + src[t]] : 0.0;
+    }
+}
+
 /* re-stride a row-major factor from (r_old, ld_old) to ld_new and plant the AUG_RANK seed:
  * new column r_old + j gets 1/sqrt(dr) at row j (j < min(n, dr))      lorads_solver.c:1096-1106,1180-1214 */
 __global__ void __launch_bounds__(LGPU_TPB) k_restride_aug(int64_t n, int r_old, int ld_old, int r_new, int ld_new,
                                                            const double *__restrict__ src, double *__restrict__ dst,
-                                                           int plant, int64_t n_glob, int64_t row_lo)
+                                                           int plant, int64_t n_glob, int64_t row_lo,
+                                                           const int32_t *__restrict__ iperm)
 {
     /* n rows of this rank, global rows row_lo .. row_lo + n of a cone of dimension n_glob */
     const int64_t total = n * (int64_t)ld_new;
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_restride_aug(int64_t n, int r_old,
         const int col = (int)(i - row * ld_new);
         double v = 0.0;
         if (col < r_old) v = src[(size_t)row * ld_old + col];
-        else if (plant && col < r_new && (int64_t)(col - r_old) == row + row_lo) v = seed;
+        else if (plant && col < r_new && (int64_t)(col - r_old) == (iperm ? (int64_t)iperm[row + row_lo] : row + row_lo)) v = seed;
         dst[i] = v;
     }
 }

@@ -228,6 +228,12 @@ struct ConeLayout {
     std::vector<int32_t> d_row; std::vector<double> d_val; /* diag_only: row and value per constraint */
     std::vector<double> mc_val;                         /* diag_only: C per full-CSR entry */
     std::vector<int32_t> rc_ptr, rc_gid; std::vector<double> rc_a; /* diag_only: row -> constraints */
+    /* row relabelling for gather locality (fused layout only): device row perm[i] holds the caller's row i; the arrays
+     * above that carry ROW labels (f_ptr/f_col, d_row, rc_*) are in the new labels, slot numbers are never touched, and
+     * dev_pat_row/dev_pat_col are the pattern's labels as the device kernels need them (pat_row/pat_col stay the caller's) */
+    bool reordered = false;
+    double window_hits_before = 0.0, window_hits_after = 0.0; /* share of CSR entries within +-65536 rows of the diagonal */
+    std::vector<int32_t> perm, iperm, dev_pat_row, dev_pat_col;
     /* row-block partition (world > 1): this rank's slices and the exchange plan */
     bool partitioned = false, use_halo = false;
     int64_t lo = 0, hi = 0, rows_per_rank = 0, halo_rows = 0, send_rows = 0;
@@ -237,6 +243,51 @@ struct ConeLayout {
     std::vector<int32_t> lf_ptr, lf_col, lrc_ptr, lrc_gid;
     std::vector<double> lmc_val, lrc_a;
 };
+
+/* Breadth-first relabelling of the rows of a symmetric CSR (Cuthill-McKee without the degree sort): vertices that are
+ * adjacent in the graph get nearby labels, so the factor rows a CSR row gathers lie within a narrow window -- L2 hits
+ * instead of DRAM reads for the sparse product, thin halos for the row-block partition.  Gives up early on graphs without
+ * locality (expander-like: the frontier passes 1/16 of all vertices within a few levels), where no labelling helps.
+ * reference: none (the reference walks its entries in file order, lorads_sdp_data.c:750-763). */
+static bool bfs_relabel(int64_t n, const std::vector<int32_t> &fp, const std::vector<int32_t> &fc, std::vector<int32_t> &perm)
+{
+    perm.assign((size_t)n, -1);
+    std::vector<int32_t> order;
+    order.reserve((size_t)n);
+    int64_t next_seed = 0;
+    while ((int64_t)order.size() < n) {
+        while (perm[next_seed] >= 0) ++next_seed;
+        size_t level_begin = order.size();
+        perm[next_seed] = (int32_t)order.size();
+        order.push_back((int32_t)next_seed);
+        while (level_begin < order.size()) {
+            const size_t level_end = order.size();
+            for (size_t q = level_begin; q < level_end; ++q) {
+                const int32_t v = order[q];
+                for (int32_t e = fp[v]; e < fp[v + 1]; ++e) {
+                    const int32_t u = fc[e];
+                    if (perm[u] < 0) { perm[u] = (int32_t)order.size(); order.push_back(u); }
+                }
+            }
+            if ((int64_t)(order.size() - level_end) > std::max<int64_t>(n / 16, 1024)) return false; /* no locality to find */
+            level_begin = level_end;
+        }
+    }
+    return true;
+}
+static double window_hit_share(int64_t n, const std::vector<int32_t> &fp, const std::vector<int32_t> &fc, const int32_t *perm)
+{
+    const int64_t W = 65536;
+    int64_t hit = 0, tot = 0;
+    const int64_t stride = std::max<int64_t>(1, n / 200000); /* a sample of the rows is enough */
+    for (int64_t i = 0; i < n; i += stride)
+        for (int32_t e = fp[i]; e < fp[i + 1]; ++e) {
+            const int64_t a = perm ? perm[i] : i, b = perm ? perm[fc[e]] : fc[e];
+            hit += (a - b <= W && b - a <= W);
+            ++tot;
+        }
+    return tot ? (double)hit / (double)tot : 1.0;
+}
 
 /* returns 0, or 1 with a message in err */
 static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int64_t *idx_in, const double *val_in, int world,
@@ -524,6 +575,57 @@ static int build_cone_layout(int64_t n, int64_t m, const int64_t *beg, const int
         });
     }
     lap("full CSR");
+    /* Row relabelling (fused MaxCut-type layout, factors larger than the L2): LORADS_REORDER=1 forces it, =0 forbids it,
+     * default: applied when it raises the share of near-diagonal entries by more than 0.15. */
+    {
+        int want = -1;
+        if (const char *rv = getenv("LORADS_REORDER")) want = atoi(rv);
+        const bool candidate = diag_only && mA == m && single_cone_no_lp && n >= 4 && !L.dense; /* dense kernels address rows by position */
+        if (candidate && want != 0 && (want == 1 || n >= (int64_t)1 << 18)) {
+            std::vector<int32_t> perm;
+            const bool found = bfs_relabel(n, f_ptr, f_col, perm);
+            if (found || want == 1) {
+                if (!found) { /* forced on a graph without locality: finish the labelling in index order */
+                    int32_t nxt = 0;
+                    std::vector<uint8_t> used((size_t)n, 0);
+                    for (int64_t i = 0; i < n; ++i) if (perm[i] >= 0) used[perm[i]] = 1;
+                    for (int64_t i = 0; i < n; ++i)
+                        if (perm[i] < 0) { while (used[nxt]) ++nxt; perm[i] = nxt; used[nxt] = 1; }
+                }
+                L.window_hits_before = window_hit_share(n, f_ptr, f_col, nullptr);
+                L.window_hits_after = window_hit_share(n, f_ptr, f_col, perm.data());
+                if (want == 1 || L.window_hits_after > L.window_hits_before + 0.15) {
+                    L.reordered = true;
+                    L.perm.swap(perm);
+                    L.iperm.resize((size_t)n);
+                    for (int64_t i = 0; i < n; ++i) L.iperm[L.perm[i]] = (int32_t)i;
+                    /* CSR in the new labels: new row a = perm[i] takes row i's entries, columns relabelled and sorted */
+                    std::vector<int32_t> np((size_t)n + 1, 0), nc((size_t)L.nnzF), ns((size_t)L.nnzF);
+                    for (int64_t a = 0; a < n; ++a) np[a + 1] = f_ptr[L.iperm[a] + 1] - f_ptr[L.iperm[a]];
+                    par_prefix(T, np);
+                    par_ranges(T, n, [&](int, int64_t lo, int64_t hi) {
+                        std::vector<std::pair<int32_t, int32_t>> row;
+                        for (int64_t a = lo; a < hi; ++a) {
+                            const int32_t i = L.iperm[a];
+                            row.clear();
+                            for (int32_t e = f_ptr[i]; e < f_ptr[i + 1]; ++e) row.emplace_back(L.perm[f_col[e]], f_slot[e]);
+                            std::sort(row.begin(), row.end());
+                            int32_t o = np[a];
+                            for (auto &pr : row) { nc[o] = pr.first; ns[o] = pr.second; ++o; }
+                        }
+                    });
+                    f_ptr.swap(np); f_col.swap(nc); f_slot.swap(ns);
+                    for (int64_t t = 0; t < mA; ++t) L.d_row[t] = L.perm[L.d_row[t]];
+                    L.dev_pat_row.resize((size_t)nnzP);
+                    L.dev_pat_col.resize((size_t)nnzP);
+                    par_ranges(T, nnzP, [&](int, int64_t lo, int64_t hi) {
+                        for (int64_t k = lo; k < hi; ++k) { L.dev_pat_row[k] = L.perm[L.pat_row[k]]; L.dev_pat_col[k] = L.perm[L.pat_col[k]]; }
+                    });
+                }
+            }
+        }
+    }
+    lap("relabel");
     if (diag_only) {
         /* fused path layout.  The diagonal entry of every CSR row goes LAST (the others stay sorted by column): the
          * sparse product's walk then ends on the row's own factor row, which is exactly what its <X_i, (C X)_i> epilogue

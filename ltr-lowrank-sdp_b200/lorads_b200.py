@@ -116,6 +116,7 @@ def lib() -> ctypes.CDLL:
         "lgpu_set_fused_path": (i, [_vp, i]),
         "lgpu_uses_fused_path": (i, [_vp]),
         "lgpu_uses_peer_exchange": (i, [_vp]),
+        "lgpu_cone_reorder_info": (i, [_vp, i, _c_dp]),
         "lgpu_set_carried_dots": (i, [_vp, i]),
         "lgpu_set_dense_tensor_path": (i, [_vp, i]),
         "lgpu_lbfgs_push": (i, [_vp, d]),
@@ -332,6 +333,11 @@ class Context:
         """join the NCCL communicator of a row-block partitioned run (before load())"""
         assert len(unique_id) == 128
         self._ck(self._L.lgpu_comm_init(self._h, unique_id, int(rank), int(world)), "lgpu_comm_init")
+
+    def reorder_info(self, cone: int = 0) -> dict:
+        out = np.zeros(3)
+        self._ck(self._L.lgpu_cone_reorder_info(self._h, int(cone), out.ctypes.data_as(_c_dp)), "lgpu_cone_reorder_info")
+        return {"applied": bool(out[0]), "window_share_before": float(out[1]), "window_share_after": float(out[2])}
 
     def uses_peer_exchange(self) -> bool:
         return bool(self._L.lgpu_uses_peer_exchange(self._h))
