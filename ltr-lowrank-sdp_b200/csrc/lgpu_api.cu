@@ -191,8 +191,36 @@ static SlotSpec<1> slot1(int s, int acc)
     return sp;
 }
 
+/* Scalars back to the host.  The plain way -- a device-to-host copy through the copy engine plus a stream synchronise --
+ * costs 15-20 us per read-back, and an ALM inner iteration has two of them; on the latency-bound instances (n <= 2e4) that
+ * was a quarter of the iteration.  Fast path: a one-warp kernel at the end of the stream stores the values into the pinned,
+ * device-mapped mirror (ctx->hsc) and then a sequence number (system-wide fence in between); the host spins on the number.
+ * A stream error is noticed by polling cudaStreamQuery now and then.  LORADS_FAST_FETCH=0 selects the plain way. */
+__global__ void __launch_bounds__(32) k_publish(const double *__restrict__ src, double *dst_host, int count,
+                                                unsigned long long *flag_host, unsigned long long seq)
+{
+    for (int k = threadIdx.x; k < count; k += 32) dst_host[k] = src[k];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) *(volatile unsigned long long *)flag_host = seq;
+}
 static int fetch_scalars(lgpu_ctx *ctx, int first, int count)
 {
+    if (ctx->fast_fetch && ctx->hsc_dev != nullptr) {
+        const unsigned long long seq = ++ctx->fetch_seq;
+        k_publish<<<1, 32, 0, ctx->stream>>>(ctx->dsc + first, ctx->hsc_dev + first, count, ctx->hflag_dev, seq);
+        volatile unsigned long long *flag = ctx->hflag;
+        for (unsigned long long spins = 1;; ++spins) {
+            if (*flag == seq) break;
+            if ((spins & 0x3fff) == 0) {
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q == cudaSuccess) { if (*flag == seq) break; }
+                else if (q != cudaErrorNotReady) LGPU_FAIL(ctx, "%s:%d stream failed while waiting for scalars: %s", __FILE__, __LINE__, cudaGetErrorString(q));
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE); /* the values were stored before the number: read them after it */
+        return 0;
+    }
     CU(ctx, cudaMemcpyAsync(ctx->hsc + first, ctx->dsc + first, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -601,6 +629,10 @@ extern "C" int64_t lgpu_launch_count(const lgpu_ctx *ctx) { return ctx ? ctx->la
 
 extern "C" int lgpu_create(lgpu_ctx **out, int device)
 {
+    /* load every kernel of the library when the context is created instead of at each kernel's first launch: lazy loading
+     * put 10-20 ms of one-off work inside the timed solve of the small instances (only effective if CUDA is not yet
+     * initialised in this process, i.e. in the drop-in binary; harmless otherwise) */
+    setenv("CUDA_MODULE_LOADING", "EAGER", 0);
     *out = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -621,6 +653,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     lgpu_ctx *ctx = new lgpu_ctx();
     ctx->device = device;
     if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
+    if (const char *v = getenv("LORADS_FAST_FETCH")) ctx->fast_fetch = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
     if (const char *v = getenv("LORADS_FUSE_PUT")) ctx->fuse_put = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
@@ -630,7 +663,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->dsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
-        cudaMallocHost((void **)&ctx->hsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->hsc, sizeof(double) * (LGPU_NSCALAR + 8), cudaHostAllocMapped) != cudaSuccess ||
         cudaMalloc((void **)&ctx->partials, sizeof(double) * LGPU_MAX_REDUCE * LGPU_MAX_PARTIAL_BLOCKS) != cudaSuccess ||
         cudaMalloc((void **)&ctx->counter, sizeof(unsigned int)) != cudaSuccess) {
         g_create_err = std::string("context allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -639,7 +672,17 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     }
     cudaMemsetAsync(ctx->dsc, 0, sizeof(double) * LGPU_NSCALAR, ctx->stream);
     cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream);
-    memset(ctx->hsc, 0, sizeof(double) * LGPU_NSCALAR);
+    memset(ctx->hsc, 0, sizeof(double) * (LGPU_NSCALAR + 8));
+    /* the mirror as the device sees it, and the read-back sequence number behind it (fetch_scalars fast path) */
+    ctx->hflag = reinterpret_cast<unsigned long long *>(ctx->hsc + LGPU_NSCALAR);
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, ctx->hsc, 0) == cudaSuccess && dp != nullptr) {
+        ctx->hsc_dev = (double *)dp;
+        ctx->hflag_dev = reinterpret_cast<unsigned long long *>(ctx->hsc_dev + LGPU_NSCALAR);
+    } else {
+        cudaGetLastError();
+        ctx->hsc_dev = nullptr;
+    }
     cudaStreamSynchronize(ctx->stream);
     *out = ctx;
     return 0;
@@ -978,10 +1021,17 @@ extern "C" int lgpu_cone_upload(lgpu_ctx *ctx, int cone, const int64_t *beg, con
     c.reordered = L.reordered;
     c.window_before = L.window_hits_before;
     c.window_after = L.window_hits_after;
+    ctx->h_cperm.clear();
     if (L.reordered) {
         TRY(dev_upload(ctx, &c.perm, L.perm));
         TRY(dev_upload(ctx, &c.iperm, L.iperm));
         c.h_iperm = L.iperm;
+        /* the m-vectors live in the renumbered constraint order from here on (b was uploaded in the caller's order) */
+        ctx->h_cperm = L.cperm;
+        std::vector<double> bp((size_t)m);
+        for (int64_t k = 0; k < m; ++k) bp[L.cperm[k]] = ctx->h_b[k];
+        CU(ctx, cudaMemcpyAsync(ctx->b, bp.data(), sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     c.n = n;
     c.n_glob = n;
@@ -1263,6 +1313,8 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     ctx->gram_pair_ok[0] = ctx->gram_pair_ok[1] = false;
     ctx->epi_done = false;
     if (ctx->world > 1 && !ctx->mc && !ctx->cone_par) LGPU_FAIL(ctx, "partitioned runs use the fused MaxCut-type path only");
+    if (!ctx->mc && ctx->ncones > 0 && ctx->cones[0].reordered)
+        LGPU_FAIL(ctx, "this cone was uploaded with the row relabelling of the fused path: keep the fused path on (or set LORADS_REORDER=0)");
     if (ctx->cone_par) {
         if (ctx->mc) LGPU_FAIL(ctx, "internal: by-cone partition with the fused single-cone path");
         /* owner of every cone: greedy balance of the per-iteration operator work ~ (nnz of the pattern + of the constraints)
@@ -1479,11 +1531,17 @@ extern "C" int lgpu_set_vec(lgpu_ctx *ctx, int which, const double *v)
 {
     if (!ctx || !mvec_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> tmp;
+    if (!ctx->h_cperm.empty()) { /* renumbered constraints (row relabelling): caller's order -> device order */
+        tmp.resize((size_t)ctx->m);
+        for (int64_t k = 0; k < ctx->m; ++k) tmp[ctx->h_cperm[k]] = v[k];
+        v = tmp.data();
+    }
     CU(ctx, cudaMemcpyAsync(mvec_of(ctx, which), v, sizeof(double) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
-extern "C" int lgpu_get_vec(lgpu_ctx *ctx, int which, double *v)
+static int get_vec_device_order(lgpu_ctx *ctx, int which, double *v)
 {
     if (!ctx || !mvec_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1502,6 +1560,16 @@ extern "C" int lgpu_get_vec(lgpu_ctx *ctx, int which, double *v)
     }
     CU(ctx, cudaMemcpyAsync(v, mvec_of(ctx, which), sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lgpu_get_vec(lgpu_ctx *ctx, int which, double *v)
+{
+    if (!ctx || !mvec_of(ctx, which)) return 1;
+    if (ctx->h_cperm.empty()) return get_vec_device_order(ctx, which, v);
+    std::vector<double> tmp((size_t)ctx->m); /* renumbered constraints (row relabelling): device order -> caller's order */
+    TRY(get_vec_device_order(ctx, which, tmp.data()));
+    for (int64_t k = 0; k < ctx->m; ++k) v[k] = tmp[ctx->h_cperm[k]];
     return 0;
 }
 extern "C" int lgpu_get_rank(const lgpu_ctx *ctx, int cone, int64_t *rank)
@@ -2756,21 +2824,54 @@ static double tridiag_extreme_eig(const std::vector<double> &a, const std::vecto
     }
     return 0.5 * (lo + hi);
 }
-/* |last component| of the unit eigenvector of T_k for eigenvalue theta (three-term recurrence, rescaled as it goes):
- * times beta_k it is the residual norm of the Ritz pair */
+/* |last component| of the unit eigenvector of T_k for its eigenvalue theta; times beta_k it is the residual norm of the
+ * Ritz pair.  Two steps of inverse iteration on T_k - (theta - delta) I with a pivoted tridiagonal elimination (the
+ * dgtsv scheme).  The obvious three-term recurrence from the first component is unstable exactly where it matters: once
+ * the extreme Ritz pair has converged its last component is ~1e-9, the recurrence returns ~1e-3, and the Lanczos ran to
+ * its step limit on every instance (250-300 steps where ~50 suffice). */
 static double tridiag_last_component(const std::vector<double> &a, const std::vector<double> &b, int k, double theta)
 {
     if (k == 1) return 1.0;
-    double vm = 0.0, v = 1.0, nrm2 = 1.0;
-    for (int i = 0; i < k - 1; ++i) {
-        const double bi = (b[i] == 0.0) ? 1e-300 : b[i];
-        double vn = ((theta - a[i]) * v - (i > 0 ? b[i - 1] * vm : 0.0)) / bi;
-        vm = v;
-        v = vn;
-        nrm2 += v * v;
-        if (nrm2 > 1e200) { const double sc = 1e-100; vm *= sc; v *= sc; nrm2 *= sc * sc; }
+    double scale = 0.0;
+    for (int i = 0; i < k; ++i) scale = std::max(scale, fabs(a[i]) + (i < k - 1 ? fabs(b[i]) : 0.0));
+    scale = std::max(scale, 1e-300);
+    const double shift = theta - 1e-13 * scale;
+    std::vector<double> x((size_t)k, 1.0 / sqrt((double)k)), dl((size_t)k), d((size_t)k), du((size_t)k);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 0; i < k; ++i) { d[i] = a[i] - shift; dl[i] = du[i] = (i < k - 1) ? b[i] : 0.0; }
+        for (int i = 0; i < k - 1; ++i) {
+            if (fabs(d[i]) >= fabs(dl[i])) {
+                if (d[i] == 0.0) d[i] = 1e-300;
+                const double f = dl[i] / d[i];
+                d[i + 1] -= f * du[i];
+                x[i + 1] -= f * x[i];
+                dl[i] = 0.0; /* from here on dl[i] is the second super-diagonal of the eliminated matrix */
+            } else {
+                const double f = d[i] / dl[i];
+                d[i] = dl[i];
+                const double t = d[i + 1];
+                d[i + 1] = du[i] - f * t;
+                if (i < k - 2) { dl[i] = du[i + 1]; du[i + 1] = -f * dl[i]; }
+                else dl[i] = 0.0;
+                du[i] = t;
+                const double tx = x[i];
+                x[i] = x[i + 1];
+                x[i + 1] = tx - f * x[i + 1];
+            }
+        }
+        for (int i = 0; i < k; ++i)
+            if (fabs(d[i]) < 1e-300 * 1e16) d[i] = (d[i] < 0 ? -1.0 : 1.0) * 1e-16 * scale; /* singular to rounding: fine for inverse iteration */
+        x[k - 1] /= d[k - 1];
+        x[k - 2] = (x[k - 2] - du[k - 2] * x[k - 1]) / d[k - 2];
+        for (int i = k - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - dl[i] * x[i + 2]) / d[i];
+        double nrm = 0.0, big = 0.0;
+        for (int i = 0; i < k; ++i) big = std::max(big, fabs(x[i]));
+        if (!(big > 0.0) || !std::isfinite(big)) return 1.0; /* give up: report "not converged" */
+        for (int i = 0; i < k; ++i) { x[i] /= big; nrm += x[i] * x[i]; }
+        nrm = sqrt(nrm);
+        for (int i = 0; i < k; ++i) x[i] /= nrm;
     }
-    return fabs(v) / sqrt(nrm2);
+    return fabs(x[k - 1]);
 }
 
 /* Lanczos step: w = S q - bprev qm and alpha = <q, S q>, one warp per row of the symmetric CSR (lanes stride over the
@@ -2892,9 +2993,9 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
      * (alpha, beta) and applies the stopping test to every prefix in order, so the result is the one the step-by-step
      * test would have returned; the (at most batch - 1) surplus steps cost a few launches. */
     std::vector<double> al((size_t)kmax), be((size_t)kmax);
-    double theta = 0.0;
+    double theta = 0.0, theta_prev = 0.0;
     int checked = 0;
-    bool done = false;
+    bool done = false, have_prev = false;
     for (int k = 0; k < kmax && !done; ++k) {
         const double *qk = qptr(k);
         const double *qm = k > 0 ? qptr(k - 1) : nullptr;
@@ -2933,14 +3034,30 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
         CU(ctx, cudaMemcpyAsync(be.data() + checked, dbe + checked, sizeof(double) * (size_t)(k + 1 - checked), cudaMemcpyDeviceToHost,
                                 ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = checked; j <= k; ++j) {
+        /* The stopping test is applied to the newest prefix only: the host-side eigenvalue work per test is O(k) per
+         * bisection step, and testing all 300 prefixes cost 30-40 ms on the small instances -- several times the device time
+         * of the whole recurrence.  Running to the end of a batch costs at most 15 cheap steps and a later Ritz value is only
+         * closer to lambda_min (it converges monotonically from above).  An exhausted Krylov space (beta ~ 0) inside the batch
+         * is honoured at its own prefix. */
+        int jtest = k;
+        for (int j = checked; j <= k; ++j)
+            if (be[(size_t)j] <= 1e-14 * std::max(fabs(al[(size_t)j]), 1e-300)) { jtest = j; break; }
+        {
+            const int j = jtest;
             const double bnorm = be[(size_t)j];
             theta = tridiag_extreme_eig(al, be, j + 1, -1);
             const double top = tridiag_extreme_eig(al, be, j + 1, +1);
             const double scale = std::max(std::max(fabs(theta), fabs(top)), 1e-300);
             const double resid = bnorm * tridiag_last_component(al, be, j + 1, theta);
-            if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale) { done = true; break; }
-            if (j + 1 >= kmax) {
+            /* converged: the Ritz residual is small -- or the Ritz VALUE has stopped moving over a whole batch while the
+             * residual is inside the reference's own ARPACK tolerance (1e-2, lorads_sdp_conic.c:1668): at a solution the
+             * slack matrix has a cluster of ~rank eigenvalues at zero, the vector of one of them never settles (residual
+             * stuck near 1e-4) although its value did long ago, and the recurrence ran to its 300-step limit */
+            const bool stalled = have_prev && fabs(theta - theta_prev) <= 1e-10 * scale && resid <= 1e-2 * scale;
+            theta_prev = theta;
+            have_prev = true;
+            if (resid <= 1e-6 * scale || bnorm <= 1e-14 * scale || jtest < k || stalled) done = true;
+            else if (k + 1 >= kmax) {
                 /* not converged: a Ritz value is only an UPPER bound of lambda_min, which would under-report the dual
                  * infeasibility; report the residual-corrected value (an eigenvalue lies within `resid` of theta) and say so */
                 if (kmax < n) {
@@ -2949,7 +3066,6 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
                     theta -= resid;
                 }
                 done = true;
-                break;
             }
         }
         checked = k + 1;
@@ -3104,11 +3220,16 @@ extern "C" int lgpu_op_auv(lgpu_ctx *ctx, int cone, int64_t r, const double *U, 
         const int32_t *gid = c.con_gid;
         const double *cv = c.cv;
         launch_map(ctx, c.mA, [=] __device__(int64_t q) { out[gid[q]] = cv[q]; });
-        cudaError_t e = cudaMemcpyAsync(constr_val, out, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost, ctx->stream);
+        std::vector<double> tmp; /* renumbered constraints (row relabelling): device order -> caller's order below */
+        if (!ctx->h_cperm.empty()) tmp.resize((size_t)ctx->m);
+        cudaError_t e = cudaMemcpyAsync(tmp.empty() ? constr_val : tmp.data(), out, sizeof(double) * ctx->m, cudaMemcpyDeviceToHost,
+                                        ctx->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = 1; }
-        if (!rc) rc = fetch_scalars(ctx, SC_OBJ, 1);
+        if (!rc) rc = fetch_scalars(ctx, SC_OBJ, 1); /* stream-ordered after the copy */
         if (!rc && obj) *obj = ctx->hsc[SC_OBJ];
+        if (!rc && !tmp.empty())
+            for (int64_t k = 0; k < ctx->m; ++k) constr_val[k] = tmp[ctx->h_cperm[k]];
     }
     op_free(&t);
     return rc;
@@ -3116,6 +3237,13 @@ extern "C" int lgpu_op_auv(lgpu_ctx *ctx, int cone, int64_t r, const double *U, 
 
 static int op_upload_w(lgpu_ctx *ctx, const double *w)
 {
+    if (!ctx->h_cperm.empty()) { /* renumbered constraints (row relabelling): caller's order -> device order */
+        std::vector<double> tmp((size_t)ctx->m);
+        for (int64_t k = 0; k < ctx->m; ++k) tmp[ctx->h_cperm[k]] = w[k];
+        CU(ctx, cudaMemcpyAsync(ctx->mtmp, tmp.data(), sizeof(double) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     CU(ctx, cudaMemcpyAsync(ctx->mtmp, w, sizeof(double) * ctx->m, cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }

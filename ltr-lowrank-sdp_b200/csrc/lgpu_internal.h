@@ -179,6 +179,7 @@ struct lgpu_ctx {
     std::vector<DevCone> cones;
     DevLp lp;
     std::vector<double> h_b;
+    std::vector<int32_t> h_cperm; /* non-empty: device m-vectors are in renumbered constraint order, cperm[k] = device id of k */
     double b_nrm1 = 0, b_nrm2 = 0, b_nrminf_q = 0;
 
     /* m-vectors */
@@ -249,7 +250,11 @@ struct lgpu_ctx {
 
     /* scalars and reduction scratch */
     double *dsc = nullptr;      /* device scalars */
-    double *hsc = nullptr;      /* pinned host mirror */
+    double *hsc = nullptr;      /* pinned host mirror (device-mapped) */
+    double *hsc_dev = nullptr;  /* the mirror's device address */
+    unsigned long long *hflag = nullptr, *hflag_dev = nullptr; /* read-back sequence number, host / device address */
+    unsigned long long fetch_seq = 0;
+    bool fast_fetch = true;
     double *partials = nullptr; /* [LGPU_MAX_REDUCE * LGPU_MAX_PARTIAL_BLOCKS] */
     unsigned int *counter = nullptr;
     /* live per-launch timing */

@@ -82,7 +82,12 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl")
-    if os.environ.get("LORADS_TEST_GRAPH", "random") == "torus":
+    if os.environ.get("LORADS_TEST_GRAPH", "random") == "torus_relabelled":
+        n, r, iters = 101 * 199, 20, 25
+        ei, ej, w = lb.torus_graph(101, 199, 81)
+        lab = np.random.default_rng(81).permutation(n)
+        ei, ej = lab[ei], lab[ej]
+    elif os.environ.get("LORADS_TEST_GRAPH", "random") == "torus":
         n, r, iters = 101 * 199, 20, 25  # structured: thin halos (the library picks the halo exchange by itself)
         ei, ej, w = lb.torus_graph(101, 199, 81)
     else:

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("world,graph,halo,peer", [
     (2, "random", "0", None), (2, "random", "1", None), (2, "random", "1", "0"), (2, "torus", None, None), (2, "torus", None, "0"),
     (4, "random", None, None), (4, "torus", None, None), (4, "torus", None, "0"), (8, "random", None, None), (8, "random", None, "0"),
-    (8, "torus", None, None)])
+    (8, "torus", None, None), (2, "torus_relabelled", None, None), (4, "torus_relabelled", None, "0")])
 def test_partitioned_run_matches_single_gpu(built, world, graph, halo, peer):
     """Row exchange: all-gather of every row (LORADS_HALO=0), the referenced rows only (=1), or the library's own choice
     (unset).  Transport: peer-memory PUT + one-shot scalar all-reduce from our own kernels (default) or NCCL
@@ -23,6 +23,11 @@ def test_partitioned_run_matches_single_gpu(built, world, graph, halo, peer):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, LORADS_TEST_GRAPH=graph)
+    env.pop("LORADS_REORDER", None)
+    if graph == "torus_relabelled":
+        # scrambled vertex labels + forced breadth-first relabelling: partition, halos and PUT lists in the new labels,
+        # factors in and out in the caller's order (scattered rows per rank)
+        env["LORADS_REORDER"] = "1"
     env.pop("LORADS_HALO", None)
     env.pop("LORADS_PEER", None)
     if halo is not None:

@@ -503,6 +503,77 @@ def test_step_and_product_kernel_variants_agree(lb, monkeypatch, n, r):
         assert rel(o[1], outs[0][1]) < 1e-11 and rel(o[2], outs[0][2]) < 1e-11 and rel(o[3], outs[0][3]) < 1e-9
 
 
+def _scrambled_torus(lb, rows, cols, seed):
+    ei, ej, w = lb.torus_graph(rows, cols, seed)
+    lab = np.random.default_rng(seed).permutation(rows * cols)
+    return rows * cols, lab[ei], lab[ej], w
+
+
+@pytest.mark.parametrize("graph", ["scrambled_torus", "random", "hub"])
+def test_row_relabelling_is_invisible_at_the_abi(lb, monkeypatch, graph):
+    """The breadth-first row relabelling of the fused layout (gather locality) against the same run without it: factors
+    go in and come out in the caller's row order, so trajectories, returned factors, m-vectors, operator entry points, the
+    rank-augmentation seed rows and the dual infeasibility must not change beyond rounding."""
+    if graph == "scrambled_torus":
+        n, ei, ej, w = _scrambled_torus(lb, 60, 70, 5)
+    elif graph == "random":
+        n = 5003
+        ei, ej, w = lb.random_graph(n, 4, 9)
+        w = np.random.default_rng(9).choice([-1.0, 1.0], size=len(ei))
+    else:
+        n = 3001
+        rng = np.random.default_rng(4)
+        key = np.unique(np.concatenate([np.arange(1, n), rng.integers(1, n, 4 * n) * n + rng.integers(1, n, 4 * n)]))
+        ei, ej = key // n, key % n
+        keep = ei < ej
+        ei, ej = ei[keep], ej[keep]
+        w = rng.choice([-1.0, 1.0], size=len(ei))
+    p = lb.maxcut_problem(n, ei, ej, w)
+    r = 11
+    rng = np.random.default_rng(n)
+    R0 = rng.random((n, r)) - rng.random((n, r))
+    Xop = rng.normal(size=(n, 5))
+    wv = rng.normal(size=n)
+    rho = 1.0 / np.sqrt(n)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LORADS_REORDER", mode)
+        ctx = lb.Context(0).load(p)
+        info = ctx.reorder_info(0)
+        assert info["applied"] == (mode == "1")
+        if mode == "1" and graph == "scrambled_torus":
+            assert info["window_share_after"] > 0.99            # a 60 x 70 torus: every neighbour within the window
+        Y = ctx.op_wsum_mulrk(0, wv, Xop, True)
+        cv, obj = ctx.op_auv(0, Xop, Xop)
+        ctx.alloc_vars([r], 2)
+        assert ctx.uses_fused_path
+        ctx.set_factor(lb.R, 0, R0)
+        assert np.array_equal(ctx.get_factor(lb.R, 0), R0)       # layout round trip is exact
+        ctx.init_constr_val(lb.PAIR_RR)
+        ctx.alm_cal_grad(rho)
+        hist = []
+        for it in range(8):
+            ctx.lbfgs_direction(it)
+            terms = ctx.alm_linesearch_terms(rho)
+            _, tau = _line_search(lb, rho, terms)
+            hist.append((tau,) + tuple(terms) + ctx.alm_inner_update(rho, tau))
+        Rf, Gf, cvs = ctx.get_factor(lb.R, 0), ctx.get_factor(lb.GRAD, 0), ctx.get_vec(lb.VEC_CONSTR_SUM)
+        dinf = ctx.dual_infeasibility()
+        ctx.aug_rank([r + 4])
+        Ra = ctx.get_factor(lb.R, 0)
+        assert np.array_equal(Ra[:, :r], Rf)
+        seed = np.zeros((n, 4))
+        seed[np.arange(4), np.arange(4)] = 0.5
+        assert np.array_equal(Ra[:, r:], seed)                   # AUG_RANK plants at the CALLER's rows 0..3
+        outs[mode] = (np.array(hist), Rf, Gf, cvs, Y, cv, obj, dinf)
+        ctx.close()
+    a, b = outs["1"], outs["0"]
+    assert np.all(np.abs(a[0] - b[0]) <= 1e-9 * np.abs(b[0]) + 1e-300)
+    assert rel(a[1], b[1]) < 1e-10 and rel(a[2], b[2]) < 1e-9 and rel(a[3], b[3]) < 1e-10
+    assert rel(a[4], b[4]) < KTOL and rel(a[5], b[5]) < KTOL and abs(a[6] - b[6]) <= KTOL * abs(b[6])
+    assert abs(a[7] - b[7]) <= 1e-6 * (1.0 + abs(b[7]))
+
+
 def test_fused_path_tracks_general_path_at_c3_scale(lb):
     """A/B at the G81-like size (n = 20000, rank 20): 40 ALM inner iterations + dual update + 1 ADMM sweep on the
     fused MaxCut-type path and on the general path from the same start; trajectories must agree far inside the
