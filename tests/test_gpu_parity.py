@@ -571,7 +571,7 @@ def test_row_relabelling_is_invisible_at_the_abi(lb, monkeypatch, graph):
     assert np.all(np.abs(a[0] - b[0]) <= 1e-9 * np.abs(b[0]) + 1e-300)
     assert rel(a[1], b[1]) < 1e-10 and rel(a[2], b[2]) < 1e-9 and rel(a[3], b[3]) < 1e-10
     assert rel(a[4], b[4]) < KTOL and rel(a[5], b[5]) < KTOL and abs(a[6] - b[6]) <= KTOL * abs(b[6])
-    assert abs(a[7] - b[7]) <= 1e-6 * (1.0 + abs(b[7]))
+    assert abs(a[7] - b[7]) <= 1e-5 * (1.0 + abs(b[7]))   # two Lanczos runs from different start vectors (the hash is by row label)
 
 
 def test_fused_path_tracks_general_path_at_c3_scale(lb):

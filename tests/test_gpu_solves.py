@@ -3,12 +3,13 @@ file, flags and seed: BASELINE configs[0] G1, the configs[2] stand-in (100 x 200
 with the reference that BASELINE configs[3] names (MC_500, checker_1.5, ice_2.0, p_auss2_3.0, cphil12) plus G11.
 
 Reference numbers come from tests/golden/bifurcation.json, written in the build container by tests/tools/bifurcation.py
-from runs of oracle/_ref/lorads_ref and oracle/_ref/lorads_ref_fma (the same sources built with FMA contraction).  That
-file also says on which instances the reference agrees with ITSELF within north-star's tolerance ("stable"):
+from five runs of the unmodified reference per instance (oracle/_ref/lorads_ref, oracle/_ref/lorads_ref_fma = the same
+sources built with FMA contraction, and lorads_ref with three other OpenBLAS kernel sets).  That file also says on which
+instances the reference agrees with ITSELF within north-star's tolerance ("stable"):
   * stable instance  -> our run must meet north-star: ALM inner iterations +-5 %, primal objective 1e-6 relative,
     same termination status, same starting rank (LORADSDetermineRank) and final rank;
-  * otherwise        -> same termination status, starting rank, and an objective no further from the reference's than
-    five times the distance between the reference's own two builds; iteration count inside [1/5, 5] x.
+  * otherwise        -> same termination status, starting rank, an objective inside the range the reference's own five
+    runs span (widened by that range) and an iteration count within [1/2 min, 2 max] of theirs.
 The quick instances are also run with the reference binary live on this box (the stored numbers must reproduce)."""
 import json
 import os
@@ -77,7 +78,7 @@ def test_whole_solve_matches_reference(built, tmp_path, verdicts, name):
         pytest.skip(f"{path} is not staged on this box (tests/tools/real_instances.py stage)")
     v = verdicts[name]
     assert v["flags"] == " ".join(flags)
-    ref, fma = v["ref"], v["ref_fma"]
+    ref = v["ref"]
     jf = tmp_path / "out.json"
     out = lb.run_solver([path] + flags + ["--timeSecLimit", "300", "--jsonfile", str(jf)], timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -95,9 +96,10 @@ def test_whole_solve_matches_reference(built, tmp_path, verdicts, name):
         if ref["admm"] is not None:
             assert mine["admm"] is not None and abs(mine["admm"] - ref["admm"]) <= max(2, 0.1 * ref["admm"]), (mine["admm"], ref["admm"])
     else:
-        spread = abs(ref["obj"] - fma["obj"])
-        assert abs(mine["obj"] - ref["obj"]) <= 5 * spread + 1e-6 * scale, (mine["obj"], ref["obj"], fma["obj"])
-        assert 0.2 * ref["alm_inner"] <= mine["alm_inner"] <= 5 * ref["alm_inner"], (mine["alm_inner"], ref["alm_inner"], fma["alm_inner"])
+        # the reference's own five runs span [obj_min, obj_max] and [inner_min, inner_max] (profiles/r2_bifurcation.md)
+        spread = v["obj_max"] - v["obj_min"]
+        assert v["obj_min"] - spread - 1e-6 * scale <= mine["obj"] <= v["obj_max"] + spread + 1e-6 * scale, (mine["obj"], v["obj_min"], v["obj_max"])
+        assert 0.5 * v["inner_min"] <= mine["alm_inner"] <= 2 * v["inner_max"], (mine["alm_inner"], v["inner_min"], v["inner_max"])
     # JSON contract (main.c:610): metrics the caller reads
     with open(jf) as f:
         js = json.load(f)
