@@ -223,6 +223,10 @@ int lgpu_agree_flag(lgpu_ctx *ctx, int *flag);
 /* 1 when the ranks exchange halo rows and scalar packs through peer-mapped memory (NVLink stores from our own kernels,
  * CUDA IPC), 0 when they use ncclSend/ncclRecv/ncclAllReduce (LORADS_PEER=0, no peer access, or two ranks on one GPU) */
 int lgpu_uses_peer_exchange(const lgpu_ctx *ctx);
+/* By-cone partition (several cones / LP block / general constraints on several GPUs): cones couple only through the
+ * length-m constraint vector and scalars (LORADSInitConstrValSum, lorads_alg_common.c:221-229), so each cone's operator
+ * work runs on one owner.  The map every rank derives: largest cost first onto the least loaded rank.  Pure function. */
+int lgpu_cone_owner_map(int ncones, const double *cost, int world, int *owner);
 
 #ifdef __cplusplus
 }

@@ -470,6 +470,21 @@ extern "C" int lgpu_comm_init(lgpu_ctx *ctx, const unsigned char id[128], int ra
 }
 
 extern "C" int lgpu_uses_peer_exchange(const lgpu_ctx *ctx) { return (ctx && ctx->peer) ? 1 : 0; }
+/* by-cone partition: largest cone first onto the least loaded rank (ties: lower cone index first, lower rank first) */
+extern "C" int lgpu_cone_owner_map(int ncones, const double *cost, int world, int *owner)
+{
+    if (ncones < 0 || world < 1 || (ncones > 0 && (!cost || !owner))) return 1;
+    std::vector<int> order(ncones);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load(world, 0.0);
+    for (int k : order) {
+        const int q = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        owner[k] = q;
+        load[q] += cost[k];
+    }
+    return 0;
+}
 extern "C" int lgpu_agree_flag(lgpu_ctx *ctx, int *flag)
 {
     if (!ctx || !flag) return 1;
@@ -967,6 +982,7 @@ extern "C" int lgpu_cone_layout_get(const lgpu_layout *layout, const char *name,
     LQ_ARRAY(mc_val, 8) LQ_ARRAY(rc_ptr, 4) LQ_ARRAY(rc_gid, 4) LQ_ARRAY(rc_a, 8) LQ_ARRAY(lf_ptr, 4) LQ_ARRAY(lf_col, 4)
     LQ_ARRAY(lmc_val, 8) LQ_ARRAY(lrc_ptr, 4) LQ_ARRAY(lrc_gid, 4) LQ_ARRAY(lrc_a, 8) LQ_ARRAY(send_idx, 4) LQ_ARRAY(halo_gid, 4)
     LQ_ARRAY(send_off, -8) LQ_ARRAY(send_cnt, -8) LQ_ARRAY(recv_off, -8) LQ_ARRAY(recv_cnt, -8) LQ_ARRAY(dst_off, -8)
+    LQ_ARRAY(perm, 4) LQ_ARRAY(iperm, 4) LQ_ARRAY(cperm, 4) LQ_ARRAY(dev_pat_row, 4) LQ_ARRAY(dev_pat_col, 4)
 #undef LQ_ARRAY
     if (nm == "scalars") {
         sc = {(double)L.mA, (double)L.nnzP, (double)L.nnzA, (double)L.nnzC, (double)L.nnzF, (double)L.max_con_len,
@@ -1317,19 +1333,15 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
         LGPU_FAIL(ctx, "this cone was uploaded with the row relabelling of the fused path: keep the fused path on (or set LORADS_REORDER=0)");
     if (ctx->cone_par) {
         if (ctx->mc) LGPU_FAIL(ctx, "internal: by-cone partition with the fused single-cone path");
-        /* owner of every cone: greedy balance of the per-iteration operator work ~ (nnz of the pattern + of the constraints)
-         * x rank, largest cone first; the same map on every rank */
-        std::vector<int> order(ctx->ncones);
-        std::iota(order.begin(), order.end(), 0);
-        auto cost = [&](int k) { const DevCone &d = ctx->cones[k]; return (double)(d.nnzP + d.nnzA + d.n) * (double)std::max<int64_t>(d.ld, 1); };
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
-        std::vector<double> load(ctx->world, 0.0);
-        ctx->cone_owner.assign(ctx->ncones, 0);
-        for (int k : order) {
-            const int q = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            ctx->cone_owner[k] = q;
-            load[q] += cost(k);
+        /* owner of every cone: greedy balance of the per-iteration operator work ~ (nnz of the pattern + of the constraints
+         * + rows) x padded rank; the same map on every rank (lgpu_cone_owner_map) */
+        std::vector<double> cost(ctx->ncones);
+        for (int k = 0; k < ctx->ncones; ++k) {
+            const DevCone &d = ctx->cones[k];
+            cost[k] = (double)(d.nnzP + d.nnzA + d.n) * (double)std::max<int64_t>(d.ld, 1);
         }
+        ctx->cone_owner.assign(ctx->ncones, 0);
+        lgpu_cone_owner_map(ctx->ncones, cost.data(), ctx->world, ctx->cone_owner.data());
     }
     if (ctx->mc) {
         TRY(alloc_flat(ctx, &ctx->CR));

@@ -117,6 +117,7 @@ def lib() -> ctypes.CDLL:
         "lgpu_uses_fused_path": (i, [_vp]),
         "lgpu_uses_peer_exchange": (i, [_vp]),
         "lgpu_cone_reorder_info": (i, [_vp, i, _c_dp]),
+        "lgpu_cone_owner_map": (i, [i, _c_dp, i, ctypes.POINTER(ctypes.c_int)]),
         "lgpu_set_carried_dots": (i, [_vp, i]),
         "lgpu_set_dense_tensor_path": (i, [_vp, i]),
         "lgpu_lbfgs_push": (i, [_vp, d]),
@@ -241,6 +242,15 @@ def cone_layout(p: "SdpaProblem", c: int, names: Sequence[str], world: int = 1, 
             out[nm] = dict(zip(LAYOUT_SCALARS, a.tolist())) if nm == "scalars" else a
     finally:
         L.lgpu_cone_layout_free(h)
+    return out
+
+
+def cone_owner_map(cost: Sequence[float], world: int) -> np.ndarray:
+    """owner rank of every cone in a by-cone partitioned run -- host logic, no GPU needed"""
+    c = np.ascontiguousarray(cost, dtype=np.float64)
+    out = np.zeros(len(c), dtype=np.int32)
+    if lib().lgpu_cone_owner_map(len(c), c.ctypes.data_as(_c_dp), int(world), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) != 0:
+        raise LoradsError("bad owner-map arguments")
     return out
 
 

@@ -259,3 +259,90 @@ def test_halo_plan_is_consistent_across_ranks(built, monkeypatch, graph, world):
         nl = len(L[r]["lf_ptr"]) - 1
         cols = L[r]["lf_col"]
         assert np.all((cols < nl) | ((cols >= rpr) & (cols < rpr + len(L[r]["halo_gid"]))))
+
+
+def _csr_rows(ptr, col):
+    return [np.sort(col[ptr[i]:ptr[i + 1]]) for i in range(len(ptr) - 1)]
+
+
+@pytest.mark.parametrize("graph", ["scrambled_torus", "random_forced"])
+def test_row_relabelling_is_a_consistent_permutation(built, monkeypatch, graph):
+    """bfs_relabel (lgpu_layout.h): the relabelled fused layout is the original one under a row permutation -- same graph,
+    same values per entry, diagonal last, constraints renumbered in row order -- and on a graph with locality it pulls the
+    entries to the diagonal."""
+    lb = built
+    if graph == "scrambled_torus":
+        rows, cols = 40, 50
+        ei, ej, w = lb.torus_graph(rows, cols, 3)
+        lab = np.random.default_rng(3).permutation(rows * cols)
+        n, ei, ej = rows * cols, lab[ei], lab[ej]
+    else:
+        n = 1500
+        ei, ej, w = lb.random_graph(n, 4, 11)
+        w = np.random.default_rng(11).choice([-1.0, 1.0], size=len(ei))
+    p = lb.maxcut_problem(n, ei, ej, w)
+    names = ["f_ptr", "f_col", "f_slot", "mc_val", "rc_ptr", "rc_gid", "rc_a", "d_row", "pat_row", "pat_col", "perm", "iperm", "cperm",
+             "dev_pat_row", "dev_pat_col", "con_gid", "t_gid"]
+    monkeypatch.setenv("LORADS_REORDER", "0")
+    A = lb.cone_layout(p, 0, names)
+    monkeypatch.setenv("LORADS_REORDER", "1")
+    B = lb.cone_layout(p, 0, names)
+    assert len(A["perm"]) == 0 and len(B["perm"]) == n
+    perm, iperm = B["perm"].astype(np.int64), B["iperm"].astype(np.int64)
+    assert np.array_equal(np.sort(perm), np.arange(n)) and np.array_equal(perm[iperm], np.arange(n))
+    # the pattern (slot numbering) is untouched; the device copy carries the new labels
+    assert np.array_equal(A["pat_row"], B["pat_row"]) and np.array_equal(A["pat_col"], B["pat_col"])
+    assert np.array_equal(B["dev_pat_row"], perm[B["pat_row"]]) and np.array_equal(B["dev_pat_col"], perm[B["pat_col"]])
+    # CSR: new row perm[i] holds row i's entries with relabelled columns; values travel with the entries
+    ra, rb = _csr_rows(A["f_ptr"], A["f_col"]), _csr_rows(B["f_ptr"], B["f_col"])
+    for i in range(0, n, 7):
+        assert np.array_equal(np.sort(perm[ra[i]]), rb[perm[i]])
+        ea = {int(perm[c]): v for c, v in zip(A["f_col"][A["f_ptr"][i]:A["f_ptr"][i + 1]], A["mc_val"][A["f_ptr"][i]:A["f_ptr"][i + 1]])}
+        a = int(perm[i])
+        eb = {int(c): v for c, v in zip(B["f_col"][B["f_ptr"][a]:B["f_ptr"][a + 1]], B["mc_val"][B["f_ptr"][a]:B["f_ptr"][a + 1]])}
+        assert ea == eb
+        cols_b = B["f_col"][B["f_ptr"][a]:B["f_ptr"][a + 1]]
+        if a in cols_b:
+            assert cols_b[-1] == a                       # diagonal entry last
+            assert np.all(np.diff(cols_b[:-1]) > 0)      # the others sorted by (new) column
+    # constraints renumbered in row order: the row -> constraint lists are the identity sequence
+    cperm = B["cperm"].astype(np.int64)
+    assert np.array_equal(np.sort(cperm), np.arange(p.m))
+    assert np.array_equal(B["rc_gid"], np.arange(p.m))
+    assert np.array_equal(cperm[A["con_gid"]], B["con_gid"]) and np.array_equal(cperm[A["t_gid"]], B["t_gid"])
+    # row of the caller's constraint k, in new labels, lists device constraint cperm[k]
+    for k in range(0, p.m, 11):
+        a = int(perm[A["d_row"][k]])
+        assert cperm[k] in B["rc_gid"][B["rc_ptr"][a]:B["rc_ptr"][a + 1]]
+    if graph == "scrambled_torus":
+        band_a = np.abs(np.repeat(np.arange(n), np.diff(A["f_ptr"])) - A["f_col"]).mean()
+        band_b = np.abs(np.repeat(np.arange(n), np.diff(B["f_ptr"])) - B["f_col"]).mean()
+        assert band_b < 0.1 * band_a, (band_a, band_b)
+
+
+def test_relabelling_gives_up_on_an_expander(built, monkeypatch):
+    """default mode: a uniform random graph above the size threshold is probed (the BFS frontier passes n/16 within a few
+    levels) and keeps its order; a torus of the same size with scrambled labels is relabelled"""
+    lb = built
+    monkeypatch.delenv("LORADS_REORDER", raising=False)
+    n = 1 << 18
+    ei, ej, w = lb.random_graph(n, 5, 0)
+    L = lb.cone_layout(lb.maxcut_problem(n, ei, ej, w), 0, ["perm"])
+    assert len(L["perm"]) == 0
+    ei, ej, w = lb.torus_graph(512, 512, 1)
+    lab = np.random.default_rng(1).permutation(n)
+    L = lb.cone_layout(lb.maxcut_problem(n, lab[ei], lab[ej], w), 0, ["perm"])
+    assert len(L["perm"]) == n
+
+
+def test_cone_owner_map(built):
+    """by-cone partition: largest cost first onto the least loaded rank; deterministic, every rank used when there is work"""
+    lb = built
+    cost = [5.0, 1.0, 9.0, 3.0, 3.0, 2.0]
+    own = lb.cone_owner_map(cost, 2)
+    assert own.tolist() == [1, 0, 0, 0, 1, 1] or sorted(np.bincount(own, weights=cost, minlength=2).tolist()) == [11.0, 12.0]
+    loads = np.bincount(own, weights=cost, minlength=2)
+    assert abs(loads[0] - loads[1]) <= max(cost)
+    assert np.array_equal(lb.cone_owner_map(cost, 2), own)              # deterministic
+    assert set(lb.cone_owner_map([1.0] * 8, 4).tolist()) == {0, 1, 2, 3}
+    assert lb.cone_owner_map([4.0], 8).tolist() == [0]
