@@ -69,6 +69,9 @@ typedef struct {
 int lh_read_sdpa(const char *fname, lh_sdpa *out, int quiet);
 int lh_write_sdpa_binary(const char *fname, const lh_sdpa *d);
 void lh_free_sdpa(lh_sdpa *d);
+/* features.c: hand-off to the reference's feature extractor (dataset/processor.py:246-345) from the parsed arrays */
+int lh_constraint_stats(const lh_sdpa *d, double *out /* m x 7 */, double *out_obj /* 7, or NULL */);
+int lh_constraint_rows(const lh_sdpa *d, int64_t *ptr /* m + 1 */, int64_t *rows /* or NULL to size */, int64_t *count);
 
 /* ---- phase states (reference: lorads_alm_state / lorads_admm_state, def_lorads_solver.h:198-238) */
 typedef struct {

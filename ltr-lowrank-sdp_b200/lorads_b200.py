@@ -317,6 +317,48 @@ def write_sdpa_binary(path: str, p: SdpaProblem) -> None:
         raise LoradsError(f"cannot write {path}")
 
 
+def _as_sdpa(p: SdpaProblem):
+    """an lh_sdpa view of the numpy arrays of p (the returned tuple keeps the temporaries alive)"""
+    s = _Sdpa()
+    nb = p.ncones
+    s.m, s.nBlks, s.nLpCols = p.m, nb, p.nlp
+    s.nElems = int(sum(int(b[-1]) for b in p.mat_beg) + (int(p.lp_beg[-1]) if p.nlp else 0))
+    s.blkDims = _i64(p.dims)
+    s.b = p.b.ctypes.data_as(_c_dp)
+    begs = (_c_lp * max(nb, 1))(*[_i64(a) for a in p.mat_beg])
+    idxs = (_c_lp * max(nb, 1))(*[_i64(a) for a in p.mat_idx])
+    vals = (_c_dp * max(nb, 1))(*[a.ctypes.data_as(_c_dp) for a in p.mat_elem])
+    s.matBeg, s.matIdx, s.matElem = begs, idxs, vals
+    return s, (begs, idxs, vals)
+
+
+CONSTRAINT_STATS = ("fro_norm", "nnz", "trace", "diag_norm", "gershgorin", "rows_touched", "blocks_touched")
+
+
+def constraint_stats(p: SdpaProblem):
+    """Hand-off to the reference's feature extractor (dataset/processor.py:246-345) from the parsed problem: per-constraint
+    statistics (m x 7, columns CONSTRAINT_STATS), the same seven numbers for the objective, and the constraint x row
+    incidence pattern as a CSR (ptr, rows) over the block-diagonal row numbering.  Host code, no GPU."""
+    H = host_lib()
+    H.lh_constraint_stats.restype = ctypes.c_int
+    H.lh_constraint_stats.argtypes = [ctypes.POINTER(_Sdpa), _c_dp, _c_dp]
+    H.lh_constraint_rows.restype = ctypes.c_int
+    H.lh_constraint_rows.argtypes = [ctypes.POINTER(_Sdpa), _c_lp, _c_lp, ctypes.POINTER(ctypes.c_int64)]
+    s, keep = _as_sdpa(p)
+    out = np.zeros((p.m, 7))
+    obj = np.zeros(7)
+    if H.lh_constraint_stats(ctypes.byref(s), out.ctypes.data_as(_c_dp), obj.ctypes.data_as(_c_dp)) != 0:
+        raise LoradsError("lh_constraint_stats failed")
+    ptr = np.zeros(p.m + 1, dtype=np.int64)
+    cnt = ctypes.c_int64()
+    if H.lh_constraint_rows(ctypes.byref(s), _i64(ptr), None, ctypes.byref(cnt)) != 0:
+        raise LoradsError("lh_constraint_rows failed")
+    rows = np.zeros(max(cnt.value, 1), dtype=np.int64)
+    H.lh_constraint_rows(ctypes.byref(s), _i64(ptr), _i64(rows), ctypes.byref(cnt))
+    del keep
+    return out, obj, ptr, rows[:cnt.value]
+
+
 def run_solver(argv: Sequence[str], **kw) -> subprocess.CompletedProcess:
     """Run the drop-in binary exactly as benchmark.py runs the reference's (benchmark.py:240-262)."""
     if not os.path.exists(BINARY_PATH):

@@ -436,3 +436,45 @@ def test_header_is_plain_c_and_cxx(tmp_path):
         r = subprocess.run([cc, std, "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(src)],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.parametrize("name", ["multiblock_lp", "control_like_12_6", "theta_n30", "G11"])
+def test_constraint_stats_match_the_feature_extractor_formulas(built, name):
+    """lh_constraint_stats / lh_constraint_rows (hand-off to dataset/processor.py) against a scipy restatement
+    of FeatureExtractor._precompute_constraint_stats and _build_pattern_matrix (processor.py:246-345): all SDP blocks as
+    one block-diagonal symmetric matrix per constraint."""
+    import scipy.sparse as sp
+    lb = built
+    p = lb.read_sdpa(inst_path(name))
+    stats, obj, ptr, rows = lb.constraint_stats(p)
+    n = int(np.sum(p.dims))
+    offs = np.concatenate([[0], np.cumsum(p.dims)])
+
+    def matrix(c):
+        ri, ci, vv = [], [], []
+        for k in range(p.ncones):
+            nk = int(p.dims[k])
+            e = slice(int(p.mat_beg[k][c]), int(p.mat_beg[k][c + 1]))
+            idx, val = p.mat_idx[k][e], p.mat_elem[k][e]
+            j = np.floor(((2 * nk + 1) - np.sqrt((2.0 * nk + 1) ** 2 - 8.0 * idx)) / 2.0).astype(np.int64)
+            j = np.where(j * (2 * nk - j + 1) // 2 > idx, j - 1, j)
+            j = np.where((j + 1) * (2 * nk - j) // 2 <= idx, j + 1, j)
+            i = idx - j * (2 * nk - j + 1) // 2 + j
+            off = i != j
+            ri += [offs[k] + i, offs[k] + j[off]]
+            ci += [offs[k] + j, offs[k] + i[off]]
+            vv += [val, val[off]]
+        return sp.csr_matrix((np.concatenate(vv), (np.concatenate(ri), np.concatenate(ci))), shape=(n, n))
+
+    for c in list(range(0, p.m + 1, max(1, p.m // 40))) + [p.m]:
+        A = matrix(c)
+        got = obj if c == 0 else stats[c - 1]
+        diag = A.diagonal()
+        row_sums = np.abs(A).sum(axis=1).A1
+        ur = np.unique(A.tocoo().row)
+        blocks = int(np.sum((offs[:-1] <= ur.max()) & (offs[1:] > ur.min()))) if len(ur) and p.ncones > 1 else (1 if len(ur) else 0)
+        want = [np.sqrt(np.sum(A.data ** 2)), A.nnz, diag.sum(), np.linalg.norm(diag), row_sums.max() if A.nnz else 0.0, len(ur)]
+        assert np.allclose(got[:6], want, rtol=1e-13, atol=1e-13), (c, got, want)
+        assert got[6] == blocks
+        if c > 0:
+            assert np.array_equal(rows[ptr[c - 1]:ptr[c]], ur)
