@@ -669,17 +669,13 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     ctx->device = device;
     if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
     if (const char *v = getenv("LORADS_FAST_FETCH")) ctx->fast_fetch = atoi(v) != 0;
-    if (const char *v = getenv("LORADS_LANCZOS_PERSISTENT")) ctx->lanczos_persistent = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
     if (const char *v = getenv("LORADS_FUSE_PUT")) ctx->fuse_put = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
     if (const char *v = getenv("LORADS_STEP_STAGES")) ctx->step_stages = atoi(v);
     if (const char *v = getenv("LORADS_SPMM_DOT")) ctx->spmm_dot = atoi(v);
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
-        ctx->num_sms = prop.multiProcessorCount;
-        ctx->coop_ok = prop.cooperativeLaunch != 0;
-    }
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->dsc, sizeof(double) * LGPU_NSCALAR) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->hsc, sizeof(double) * (LGPU_NSCALAR + 8), cudaHostAllocMapped) != cudaSuccess ||
@@ -2944,91 +2940,6 @@ __global__ void __launch_bounds__(LGPU_TPB) k_basis_update(int64_t n, int k, con
     }
 }
 
-/* Persistent form of the recurrence for the latency-bound cones (the whole Krylov basis fits, single GPU): `nsteps`
- * Lanczos steps in ONE cooperative launch, the phases of a step separated by grid-wide barriers instead of kernel
- * boundaries (6 launches of a few microseconds of work each per step otherwise: 12-19 ms of the 24-31 ms an n = 800
- * MaxCut solve took).  Per step k:  A) w = S q_k - beta_{k-1} q_{k-1}, alpha_k = <q_k, S q_k>   B) h_j = <q_j, w>, j <= k
- * (a warp per basis vector)   C) w -= sum_j h_j q_j, |w|^2   D) q_{k+1} = w / beta_k.  Sums over the grid go through
- * `part` and are added in block order by every CTA (same bits everywhere, run to run). */
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-__device__ __forceinline__ double block_sum_256(double v, double *sh)
-{
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < LGPU_TPB / 32; ++w) t += sh[w];
-    __syncthreads();
-    return t;
-}
-__device__ __forceinline__ double grid_total(const double *part, double *sh)
-{
-    double t = 0.0;
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += LGPU_TPB) t += ((const volatile double *)part)[b];
-    return block_sum_256(t, sh);
-}
-__global__ void __launch_bounds__(LGPU_TPB) k_lanczos_persistent(int64_t n, int64_t vec, const int32_t *__restrict__ fp,
-                                                                 const int32_t *__restrict__ fc, const int32_t *__restrict__ fs,
-                                                                 const double *__restrict__ Sv, double *Q, double *w, double *h,
-                                                                 double *dal, double *dbe, double *part, int k0, int nsteps, int kmax)
-{
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sh[LGPU_TPB / 32];
-    const int lane = threadIdx.x & 31;
-    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x, gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t warps = gthreads >> 5, gwarp = gtid >> 5;
-    for (int k = k0; k < k0 + nsteps && k < kmax; ++k) {
-        const double *qk = Q + (size_t)k * vec;
-        const double *qm = k > 0 ? Q + (size_t)(k - 1) * vec : nullptr;
-        const double bprev = k > 0 ? ((volatile double *)dbe)[k - 1] : 0.0;
-        /* A */
-        double red = 0.0;
-        for (int64_t i = gwarp; i < n; i += warps) {
-            double a = 0.0;
-            for (int e = fp[i] + lane; e < fp[i + 1]; e += 32) a = fma(Sv[fs[e]], qk[fc[e]], a);
-            a = warp_sum(a);
-            if (lane == 0) {
-                red = fma(qk[i], a, red);
-                w[i] = qm ? fma(-bprev, qm[i], a) : a;
-            }
-        }
-        red = block_sum_256(red, sh);
-        if (threadIdx.x == 0) part[blockIdx.x] = red;
-        grid.sync();
-        const double alpha = grid_total(part, sh);
-        /* B */
-        for (int64_t j = gwarp; j <= k; j += warps) {
-            const double *qj = Q + (size_t)j * vec;
-            double a = 0.0;
-            for (int64_t i = lane; i < n; i += 32) a = fma(qj[i], w[i], a);
-            a = warp_sum(a);
-            if (lane == 0) h[j] = a;
-        }
-        grid.sync();
-        /* C */
-        double nn = 0.0;
-        for (int64_t i = gtid; i < n; i += gthreads) {
-            double a = w[i];
-            for (int j = 0; j <= k; ++j) a = fma(-((const volatile double *)h)[j], Q[(size_t)j * vec + i], a);
-            w[i] = a;
-            nn = fma(a, a, nn);
-        }
-        nn = block_sum_256(nn, sh);
-        if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = nn;
-        grid.sync();
-        const double beta = sqrt(grid_total(part + gridDim.x, sh));
-        /* D */
-        if (k + 1 < kmax) {
-            const double inv = beta > 0.0 ? 1.0 / beta : 0.0; /* an exhausted Krylov space yields zeros, not NaNs */
-            double *qn = Q + (size_t)(k + 1) * vec;
-            for (int64_t i = gtid; i < n; i += gthreads) qn[i] = w[i] * inv;
-        }
-        if (gtid == 0) { dal[k] = alpha; dbe[k] = beta; }
-        grid.sync();
-    }
-}
-
 /* S q for the partitioned fused layout: this rank's rows of (C - Diag(sum_k lambda_k a_k)) q into w at their GLOBAL
  * positions; q is a replicated full-length vector.  Column ids are global (all-gather mode) or local/halo ids that
  * halo_gid maps back to global rows. */
@@ -3062,12 +2973,7 @@ __global__ void __launch_bounds__(LGPU_TPB) k_lanczos_symv_part(int64_t nloc, in
  * (spectral scale of T_k).  Small problems keep the whole Krylov basis and re-orthogonalise against it (two launches per
  * step); large ones run the plain three-term recurrence, whose extreme Ritz value stays accurate without it. */
 typedef std::function<int(const double *, const double *, const double *, double *)> LanczosApply;
-struct LanczosCsr { /* the operator as a symmetric CSR with values on pattern slots: enables the persistent kernel */
-    const int32_t *fp, *fc, *fs;
-    const double *Sv;
-};
-static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const LanczosApply &apply, double *theta_out,
-                           const LanczosCsr *csr = nullptr)
+static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const LanczosApply &apply, double *theta_out)
 {
     double *dsc = ctx->dsc;
     const int kmax = (int)std::min<int64_t>(n, 300);
@@ -3102,34 +3008,7 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
     double theta = 0.0, theta_prev = 0.0;
     int checked = 0;
     bool done = false, have_prev = false;
-    /* persistent cooperative kernel for the small cones (see k_lanczos_persistent); LORADS_LANCZOS_PERSISTENT=0: per-step launches */
-    bool persistent = csr != nullptr && full && ctx->world == 1 && ctx->coop_ok && ctx->lanczos_persistent;
-    int pgrid = 0;
-    double *ppart = nullptr;
-    if (persistent) {
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lanczos_persistent, LGPU_TPB, 0) != cudaSuccess || occ < 1) persistent = false;
-        else {
-            const int64_t want = (n * 32 + LGPU_TPB - 1) / LGPU_TPB; /* a warp per row */
-            pgrid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * std::min(occ, 4)));
-            ppart = ctx->partials; /* 2 * pgrid doubles */
-            if (2 * pgrid > LGPU_MAX_REDUCE * LGPU_MAX_PARTIAL_BLOCKS) persistent = false;
-        }
-    }
     for (int k = 0; k < kmax && !done; ++k) {
-        if (persistent) {
-            /* one launch runs the next `batch` steps; k jumps to the last of them and the read-back / test below follows */
-            int k0 = k, ns = std::min(batch, kmax - k0), km = kmax;
-            int64_t nn = n, vv = vec_len;
-            const int32_t *fp = csr->fp, *fc = csr->fc, *fs = csr->fs;
-            const double *Sv = csr->Sv;
-            void *args[] = {&nn, &vv, &fp, &fc, &fs, &Sv, &Q, &w, &hbuf, &dal, &dbe, &ppart, &k0, &ns, &km};
-            {
-                Prof pr(ctx, KC_SPMM);
-                CU(ctx, cudaLaunchCooperativeKernel((const void *)k_lanczos_persistent, dim3(pgrid), dim3(LGPU_TPB), args, 0, ctx->stream));
-            }
-            k = k0 + ns - 1;
-        } else {
         const double *qk = qptr(k);
         const double *qm = k > 0 ? qptr(k - 1) : nullptr;
         TRY(apply(qk, qm, k > 0 ? dbe + (k - 1) : nullptr, w));
@@ -3159,7 +3038,6 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
         if (k + 1 < kmax) {
             double *qn = qptr(k + 1);
             launch_map(ctx, n, [=] __device__(int64_t i) { qn[i] = w[i] * dsc[SC_LANCZOS + 3]; });
-        }
         }
         if ((k + 1) % batch != 0 && k + 1 < kmax) continue;
         /* read the new coefficients back and test the prefixes checked .. k */
@@ -3275,8 +3153,7 @@ extern "C" int lgpu_dual_infeasibility(lgpu_ctx *ctx, double *sum_neg_eig)
                 n, fp, fc, fs, Sv, qk, qm, bprev_p, w, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_LANCZOS));
             return 0;
         };
-        const LanczosCsr csr = {fp, fc, fs, Sv};
-        TRY(lanczos_min_eig(ctx, n, n, apply, &theta, &csr));
+        TRY(lanczos_min_eig(ctx, n, n, apply, &theta));
         total += fabs(std::min(theta, 0.0));
     }
     if (ctx->cone_par) {

@@ -255,7 +255,6 @@ struct lgpu_ctx {
     unsigned long long *hflag = nullptr, *hflag_dev = nullptr; /* read-back sequence number, host / device address */
     unsigned long long fetch_seq = 0;
     bool fast_fetch = true;
-    bool coop_ok = false, lanczos_persistent = true; /* cooperative launches available / persistent Lanczos kernel (A/B) */
     double *partials = nullptr; /* [LGPU_MAX_REDUCE * LGPU_MAX_PARTIAL_BLOCKS] */
     unsigned int *counter = nullptr;
     /* live per-launch timing */
