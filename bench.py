@@ -551,8 +551,10 @@ def run_ours(args):
     d2h = (8.0 * n * r + world * 16.0 * n) / args.steps + world * 17 * 8
     assert np.isfinite(Rfin[::997]).all() and np.isfinite(out[2])
     e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "note": "initial factor host->device, K iterations via the C ABI with the line search on the host, final "
-                   "factor + dual + constraint values device->host; transfer bytes amortised over the K steps"}
+           "note": "through the C ABI from pinned HOST buffers, inside the timed region: initial factor host->device, K "
+                   "iterations (every step: rho and tau go down as call arguments, 17 scalars come back), final factor + dual + "
+                   "constraint values device->host.  The per-step inputs of this iterative solver are two scalars; the factor "
+                   "is the job's input/output, so its bytes are amortised over the K steps in h2d/d2h_bytes_per_step"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
