@@ -548,11 +548,11 @@ def run_ours(args):
         e2e_s = float(t[0])
     # whole-job bytes: each rank moves only its rows of the factor; the m-vectors go to / come from every rank
     h2d = (8.0 * n * r + world * 8.0 * n) / args.steps
-    d2h = (8.0 * n * r + world * 16.0 * n) / args.steps + world * 17 * 8
+    d2h = (8.0 * n * r + world * 16.0 * n) / args.steps + world * 25 * 8   # 7 line-search + 18 step scalars per iteration
     assert np.isfinite(Rfin[::997]).all() and np.isfinite(out[2])
     e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "note": "through the C ABI from pinned HOST buffers, inside the timed region: initial factor host->device, K "
-                   "iterations (every step: rho and tau go down as call arguments, 17 scalars come back), final factor + dual + "
+                   "iterations (every step: rho and tau go down as call arguments, 25 scalars come back), final factor + dual + "
                    "constraint values device->host.  The per-step inputs of this iterative solver are two scalars; the factor "
                    "is the job's input/output, so its bytes are amortised over the K steps in h2d/d2h_bytes_per_step"}
 

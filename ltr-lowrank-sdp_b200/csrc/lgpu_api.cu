@@ -669,6 +669,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     ctx->device = device;
     if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
     if (const char *v = getenv("LORADS_FAST_FETCH")) ctx->fast_fetch = atoi(v) != 0;
+    if (const char *v = getenv("LORADS_ROWDOTS")) ctx->rowdots_enabled = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
     if (const char *v = getenv("LORADS_FUSE_PUT")) ctx->fuse_put = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
@@ -777,7 +778,7 @@ static void free_vars(lgpu_ctx *ctx, bool collective = true)
     if (ctx->peer && ctx->halo != nullptr) peer_unmap_halo(ctx, collective);
     dev_free(ctx->R); dev_free(ctx->U); dev_free(ctx->V); dev_free(ctx->G); dev_free(ctx->M2); dev_free(ctx->bLin);
     dev_free(ctx->cg_r); dev_free(ctx->cg_p); dev_free(ctx->cg_Q); dev_free(ctx->stage);
-    dev_free(ctx->CR); dev_free(ctx->CD); dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
+    dev_free(ctx->CR); dev_free(ctx->CD); dev_free(ctx->rowdots); ctx->rowdots_valid = false; dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
     ctx->cr_valid = ctx->cd_valid = false;
     ctx->mc = false;
     for (auto &p : ctx->s) dev_free(p);
@@ -1343,9 +1344,11 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
         ctx->cone_owner.assign(ctx->ncones, 0);
         lgpu_cone_owner_map(ctx->ncones, cost.data(), ctx->world, ctx->cone_owner.data());
     }
+    ctx->rowdots_valid = false;
     if (ctx->mc) {
         TRY(alloc_flat(ctx, &ctx->CR));
         TRY(alloc_flat(ctx, &ctx->CD));
+        if (lbfgs_len == 2 && ctx->rowdots_enabled) TRY(dev_alloc(ctx, &ctx->rowdots, (size_t)ctx->cones[0].n_alloc * 5));
     }
     if (ctx->world > 1 && !ctx->cone_par) {
         dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
@@ -1513,6 +1516,7 @@ extern "C" int lgpu_set_factor(lgpu_ctx *ctx, int which, int cone, const double 
     CU(ctx, cudaSetDevice(ctx->device));
     DevCone &c = ctx->cones[cone];
     if (which == LGPU_R) ctx->cr_valid = false;
+    ctx->rowdots_valid = false; /* R, the gradient or a pair may have been replaced */
     if (which == LGPU_U) { ctx->cd_valid = false; ctx->epi_done = false; }
     return upload_factor(ctx, c.n, c.r, c.ld, cm, flat_of(ctx, which) + c.off, c.n_glob, c.row_lo, &c);
 }
@@ -1596,6 +1600,7 @@ extern "C" int lgpu_fill_factor_random(lgpu_ctx *ctx, int which, uint64_t seed)
     if (!ctx || !ctx->vars_ready || !flat_of(ctx, which)) return 1;
     CU(ctx, cudaSetDevice(ctx->device));
     if (which == LGPU_R) ctx->cr_valid = false;
+    ctx->rowdots_valid = false; /* R, the gradient or a pair may have been replaced */
     if (which == LGPU_U) { ctx->cd_valid = false; ctx->epi_done = false; }
     for (auto &c : ctx->cones) {
         double *p = flat_of(ctx, which) + c.off;
@@ -1969,6 +1974,7 @@ extern "C" int lgpu_alm_cal_grad(lgpu_ctx *ctx, double rho, double *lag_norm_squ
     *lag_norm_square = ctx->hsc[SC_LAG];
     ctx->gram.gg = ctx->hsc[SC_LAG];
     ctx->gram_valid = false; /* the gradient changed outside a step: <g, s_j>, <g, y_j> are stale */
+    ctx->rowdots_valid = false;
     return 0;
 }
 
@@ -1983,6 +1989,10 @@ static int mc_direction_gram(lgpu_ctx *ctx, int nn)
     const int j1 = (ctx->head - 1 + h) % h, j0 = j1 ^ 1;
     auto &gm = ctx->gram;
     const bool have = ctx->gram_valid && ctx->gram_pair_ok[j1] && (nn < 2 || ctx->gram_pair_ok[j0]);
+    /* the per-row and <C R, .> products of the last bulk step pass describe the current R, g and pairs only if nothing
+     * touched them since (same condition as the carried L-BFGS products, which a refresh pass below cannot restore) */
+    const bool rowdots = ctx->rowdots_enabled && ctx->rowdots_valid && ctx->rowdots != nullptr && ctx->gram_valid &&
+                         (nn == 0 || have) && ctx->cr_valid;
     if (nn > 0 && !have) {
         /* refresh: ten inner products in one pass over (G, s0, y0, s1, y1) */
         const double *G = ctx->G, *s1 = ctx->s[j1], *y1 = ctx->y[j1], *s0 = ctx->s[j0], *y0 = ctx->y[j0];
@@ -2045,17 +2055,31 @@ static int mc_direction_gram(lgpu_ctx *ctx, int nn)
         ctx->pending_put_x = ctx->U;
         ctx->pending_put_seq = seq;
     }
+    ctx->p1_host = 0.0;
+    if (rowdots) {
+        /* <C R, D> for D = -g + a1 y1 + a0 y0 - w0 s0 - w1 s1 from the carried (already rank-reduced) products */
+        double p1 = -gm.cr_g;
+        if (cf.nn >= 1) {
+            p1 += cf.a1 * gm.cr_y[j1];
+            if (cf.nn >= 2) { p1 += cf.a0 * gm.cr_y[j0]; p1 -= cf.w0 * gm.cr_s[j0]; }
+            p1 -= cf.w1 * gm.cr_s[j1];
+        }
+        ctx->p1_host = p1;
+    }
     {
         Prof pr(ctx, KC_MC_DIR);
+#define MC_COMBINE(PUT, RD)                                                                                                          \
+    DISPATCH_G(G, k_mc_combine<GG, PUT, RD><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG, PUT, RD>), LGPU_TPB, 0,           \
+                                               ctx->stream>>>(c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], \
+                                                              ctx->R, ctx->CR, ctx->U, c.rc_ptr, c.rc_gid, c.rc_a, ctx->q1, ctx->q2,    \
+                                                              ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0),                  \
+                                                              (PUT) ? ctx->put_dest : nullptr, pd, ctx->rowdots))
         if (put) {
-            DISPATCH_G(G, k_mc_combine<GG, true><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG, true>), LGPU_TPB, 0, ctx->stream>>>(
-                              c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], ctx->R, ctx->CR, ctx->U, c.rc_ptr,
-                              c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0), ctx->put_dest, pd));
+            if (rowdots) { MC_COMBINE(true, true); } else { MC_COMBINE(true, false); }
         } else {
-            DISPATCH_G(G, k_mc_combine<GG, false><<<grid_for(ctx, c.n * GG, (const void *)k_mc_combine<GG, false>), LGPU_TPB, 0, ctx->stream>>>(
-                              c.n, (int)c.ld, cf, ctx->G, ctx->s[j1], ctx->y[j1], ctx->s[j0], ctx->y[j0], ctx->R, ctx->CR, ctx->U, c.rc_ptr,
-                              c.rc_gid, c.rc_a, ctx->q1, ctx->q2, ctx->partials, ctx->counter, ctx->dsc, slot1(SC_P1, 0), nullptr, pd));
+            if (rowdots) { MC_COMBINE(false, true); } else { MC_COMBINE(false, false); }
         }
+#undef MC_COMBINE
     }
     ctx->defer_allreduce = false;
     ctx->epi_done = true;
@@ -2213,7 +2237,7 @@ extern "C" int lgpu_alm_linesearch_terms(lgpu_ctx *ctx, double rho, double out[7
     }
     CHECK_LAUNCH(ctx);
     TRY(fetch_scalars(ctx, SC_P1, 7));
-    out[0] = 2.0 * ctx->hsc[SC_P1];
+    out[0] = 2.0 * (ctx->hsc[SC_P1] + ((ctx->mc && ctx->epi_done) ? ctx->p1_host : 0.0));
     out[1] = ctx->hsc[SC_P2];
     for (int k = 0; k < 5; ++k) out[2 + k] = ctx->hsc[SC_LS0 + k];
     return 0;
@@ -2240,6 +2264,8 @@ extern "C" int lgpu_alm_step(lgpu_ctx *ctx, double tau)
             R[i] = fma(tau, D[i], R[i]);
         });
         ctx->cr_valid = false;
+    ctx->rowdots_valid = false;
+        ctx->rowdots_valid = false;
     }
     {
         double *cvs = ctx->cvs;
@@ -2273,6 +2299,7 @@ extern "C" int lgpu_lbfgs_push(lgpu_ctx *ctx, double tau)
     ctx->gram_pair_ok[ctx->head] = false;
     ctx->head = (ctx->head + 1) % ctx->h;
     ctx->gram_valid = false;
+    ctx->rowdots_valid = false;
     CHECK_LAUNCH(ctx);
     return 0;
 }
@@ -2298,6 +2325,7 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
      * fits the 227 KB of shared memory; very wide factors (small problems, L2-resident anyway) keep the register kernel */
     int tr = 0, nstage = 0;
     size_t bulk_smem = 0;
+    bool wrote_rowdots = false;
     if (ctx->step_bulk) {
         const int NG = LGPU_TPB / G;
         tr = ctx->step_tile_rows > 0 ? ctx->step_tile_rows : (int)std::max<int64_t>(NG, std::min<int64_t>(64, 8192 / (c.ld * 8)));
@@ -2315,9 +2343,11 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
         const int threads = LGPU_TPB + 32 * nstage;
         Prof pr(ctx, KC_MC_STEP);
         if (gram) {
-            SlotSpec<10> sp;
+            SlotSpec<15> sp;
             for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
+            for (int k = 0; k < 5; ++k) sp.slot[10 + k] = SC_CRG + k;
             sp.accumulate = 0;
+            wrote_rowdots = ctx->rowdots != nullptr;
             DISPATCH_G(G, {
                 auto kern = k_mc_step_bulk<GG, true>;
                 static size_t attr_bytes = 0;
@@ -2328,7 +2358,7 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
                 kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
                                                                ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
                                                                ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo], ctx->partials, ctx->counter,
-                                                               ctx->dsc, sp, SC_BETA0 + jn);
+                                                               ctx->dsc, sp, SC_BETA0 + jn, ctx->rowdots);
             });
         } else {
             SlotSpec<3> sp;
@@ -2343,7 +2373,7 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
                 kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
                                                                ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
                                                                ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials, ctx->counter,
-                                                               ctx->dsc, sp, SC_BETA0 + jn);
+                                                               ctx->dsc, sp, SC_BETA0 + jn, nullptr);
             });
         }
     } else if (gram) {
@@ -2375,7 +2405,8 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
                           c.rc_a, ctx->lam, ctx->b, ctx->cvs, ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials,
                           ctx->counter, ctx->dsc, sp, SC_BETA0 + jn));
     }
-    const int nsc = gram ? 10 : 3;
+    /* SC_LAG .. SC_YNYN (10), or with the carried <C R, .> products up to SC_CRYO (18, three refresh-only slots in between) */
+    const int nsc = gram ? (wrote_rowdots ? SC_CRYO - SC_LAG + 1 : 10) : 3;
     if (ctx->world > 1) {
         TRY(allreduce_scalars(ctx, SC_LAG, nsc));
         double *dsc = ctx->dsc;
@@ -2398,6 +2429,11 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
         gm.beta[jn] = 1.0 / v[SC_YS];
         gm.sg[jn] = v[SC_GSN]; gm.yg[jn] = v[SC_GYN]; gm.sg[jo] = v[SC_GSO]; gm.yg[jo] = v[SC_GYO];
         gm.so_yn = v[SC_SOYN]; gm.yo_yn = v[SC_YOYN]; gm.yy[jn] = v[SC_YNYN];
+        if (wrote_rowdots) {
+            gm.cr_g = v[SC_CRG];
+            gm.cr_s[jn] = v[SC_CRSN]; gm.cr_y[jn] = v[SC_CRYN]; gm.cr_s[jo] = v[SC_CRSO]; gm.cr_y[jo] = v[SC_CRYO];
+        }
+        ctx->rowdots_valid = wrote_rowdots && ctx->cr_updates > 0; /* a refresh of C R just above makes <C R, .> stale */
         ctx->gram_pair_ok[jn] = true;
         /* <g, .> is fresh for both pairs; the older pair's <y,y> and beta are carried from the step that formed it
          * (gram_pair_ok); otherwise the next two-pair direction refreshes everything in one pass */
@@ -2456,6 +2492,7 @@ extern "C" int lgpu_average_uv(lgpu_ctx *ctx)
     const double *U = ctx->U, *V = ctx->V;
     launch_map(ctx, ctx->N, [=] __device__(int64_t i) { R[i] = (U[i] + V[i]) / 2.0; });
     ctx->cr_valid = false;
+    ctx->rowdots_valid = false;
     CHECK_LAUNCH(ctx);
     return 0;
 }

@@ -20,9 +20,9 @@
 
 #define LGPU_NSCALAR 256
 #define LGPU_MAX_WORLD 16   /* ranks of one node */
-#define LGPU_PEER_RED 16    /* widest scalar pack of the one-shot peer all-reduce */
+#define LGPU_PEER_RED 24    /* widest scalar pack of the one-shot peer all-reduce */
 #define LGPU_MAX_PARTIAL_BLOCKS 1184 /* 148 SMs x 8 resident CTAs of 256 threads */
-#define LGPU_MAX_REDUCE 12           /* widest fused reduction (k_reduce / grid_reduce_finish) */
+#define LGPU_MAX_REDUCE 16           /* widest fused reduction (k_reduce / grid_reduce_finish) */
 
 /* device scalar slots (ctx->dsc) */
 enum {
@@ -42,6 +42,11 @@ enum {
     SC_YOYO,   /* <y_old, y_old> (refresh pass only) */
     SC_BN,     /* refresh pass only: <y_new, s_new>, <y_old, s_old> */
     SC_BO,
+    SC_CRG,    /* carried <C R, .> with g, s_new, y_new, s_old, y_old (bulk step pass): <C R, D> without reading C R again */
+    SC_CRSN,
+    SC_CRYN,
+    SC_CRSO,
+    SC_CRYO,   /* SC_LAG .. SC_CRYO stay contiguous: one fetch / one all-reduce of the step's pack */
     SC_DG,     /* <D, Grad> */
     SC_P1,     /* <C, R D^T> accumulated over cones (not yet doubled) */
     SC_P2,     /* <C, D D^T> */
@@ -242,7 +247,13 @@ struct lgpu_ctx {
     bool defer_allreduce = false; /* partitioned: keep local sums, a later call all-reduces the whole pack */
     struct {
         double gg, sg[2], yg[2], yy[2], beta[2], so_yn, yo_yn; /* indexed by ring slot; cross terms: (older, newer) */
+        double cr_g, cr_s[2], cr_y[2];                          /* <C R, g>, <C R, s_j>, <C R, y_j> */
     } gram;
+    /* per-row inner products <R_i, g_i>, <R_i, s_new_i>, <R_i, y_new_i>, <R_i, s_old_i>, <R_i, y_old_i> written by the bulk
+     * step pass ([n_alloc][5]); with them and the carried <C R, .> the direction pass needs neither R nor C R */
+    double *rowdots = nullptr;
+    bool rowdots_valid = false, rowdots_enabled = true;
+    double p1_host = 0.0; /* <C R, D> formed on the host from the carried products (added to dsc[SC_P1], which is then zero) */
     bool epi_done = false; /* q1, q2 and <C, R D^T> already produced by the direction pass for the current D */
     int h = 0, head = 0;
     std::vector<double *> s, y;

@@ -1099,7 +1099,10 @@ struct PublishSeq { /* runs in the finishing thread of the grid, after every CTA
         for (int j = 0; j < pd.npeer; ++j) st_release_sys_u64(pd.flag[j], pd.seq);
     }
 };
-template <int G, bool PUT>
+/* ROWDOTS: <R_i, D_i> comes from the per-row products the bulk step pass left (rowdots[i][0..4] against g, s1, y1, s0, y0)
+ * combined with the direction's coefficients, and <C R, D> from the carried global products on the host: the pass then reads
+ * neither R nor C R (6 F instead of 8 F; rowdots adds 40 bytes per row) */
+template <int G, bool PUT, bool ROWDOTS>
 __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirCoef cf, const double *__restrict__ Gd,
                                                          const double *__restrict__ s1, const double *__restrict__ y1,
                                                          const double *__restrict__ s0, const double *__restrict__ y0,
@@ -1108,7 +1111,8 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
                                                          const int32_t *__restrict__ rcgid, const double *__restrict__ rca,
                                                          double *__restrict__ q1, double *__restrict__ q2, double *partials,
                                                          unsigned int *counter, double *dsc, SlotSpec<1> spec,
-                                                         const int32_t *__restrict__ dest, PeerDirect pd)
+                                                         const int32_t *__restrict__ dest, PeerDirect pd,
+                                                         const double *__restrict__ rowdots)
 {
     const int lane = threadIdx.x % G;
     const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / G;
@@ -1144,14 +1148,26 @@ __global__ void __launch_bounds__(LGPU_TPB) k_mc_combine(int64_t n, int ld, DirC
                         if (slot >= 0) reinterpret_cast<double2 *>(pd.dst[j])[(size_t)slot * ld2 + c] = d;
                     }
                 }
-                const double2 r = reinterpret_cast<const double2 *>(Rm)[w];
-                const double2 cr = reinterpret_cast<const double2 *>(CR)[w];
-                rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
+                if (!ROWDOTS) {
+                    const double2 r = reinterpret_cast<const double2 *>(Rm)[w];
+                    const double2 cr = reinterpret_cast<const double2 *>(CR)[w];
+                    rd = fma(r.x, d.x, rd); rd = fma(r.y, d.y, rd);
+                    red[0] = fma(cr.x, d.x, red[0]); red[0] = fma(cr.y, d.y, red[0]);
+                }
                 dd = fma(d.x, d.x, dd); dd = fma(d.y, d.y, dd);
-                red[0] = fma(cr.x, d.x, red[0]); red[0] = fma(cr.y, d.y, red[0]);
             }
-        rd = group_sum<G>(rd);
+        if (!ROWDOTS) rd = group_sum<G>(rd);
         dd = group_sum<G>(dd);
+        if (ROWDOTS && live && lane == 0) {
+            /* <R_i, D_i> with D = -g + a1 y1 + a0 y0 - w0 s0 - w1 s1 (the axpy sequence above, applied to the row products) */
+            const double *o = rowdots + (size_t)i * 5;
+            rd = -o[0];
+            if (cf.nn >= 1) {
+                rd = fma(cf.a1, o[2], rd);
+                if (cf.nn >= 2) { rd = fma(cf.a0, o[4], rd); rd = fma(-cf.w0, o[3], rd); }
+                rd = fma(-cf.w1, o[1], rd);
+            }
+        }
         if (live && lane == 0)
             for (int t = rcptr[i]; t < rcptr[i + 1]; ++t) {
                 const double a = rca[t];
@@ -1330,10 +1346,12 @@ k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, do
                const double *__restrict__ rca, const double *__restrict__ lam, const double *__restrict__ b,
                double *__restrict__ cvs, const double *__restrict__ q1, const double *__restrict__ q2, double *__restrict__ M1,
                const double *__restrict__ so, const double *__restrict__ yo, double *partials, unsigned int *counter, double *dsc,
-               SlotSpec<GRAM ? 10 : 3> spec, int beta_slot)
+               SlotSpec<GRAM ? 15 : 3> spec, int beta_slot, double *__restrict__ rowdots)
 {
+    /* GRAM: reductions [10..14] = <CR, g>, <CR, s_new>, <CR, y_new>, <CR, s_old>, <CR, y_old> and, per row, the same five
+     * partners against R_i into rowdots[i][0..4]: the next direction pass gets <R_i, D_i> and <C R, D> from them */
     constexpr int NSTREAM = GRAM ? 7 : 5;
-    constexpr int NR = GRAM ? 10 : 3;
+    constexpr int NR = GRAM ? 15 : 3;
     constexpr int NG = LGPU_TPB / G;
     extern __shared__ __align__(128) unsigned char smem[];
     const int ld2 = ld >> 1;
@@ -1436,6 +1454,7 @@ k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, do
             const int rr = rb + grp;
             const bool live = rr < rows;
             double rsq = 0.0;
+            double rdot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             if (live) {
                 const double coef = scoef[rr];
                 for (int c = lane; c < ld2; c += G) {
@@ -1470,11 +1489,30 @@ k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, do
                         red[7] = fma(os.x, yv.x, red[7]); red[7] = fma(os.y, yv.y, red[7]);
                         red[8] = fma(oy.x, yv.x, red[8]); red[8] = fma(oy.y, yv.y, red[8]);
                         red[9] = fma(yv.x, yv.x, red[9]); red[9] = fma(yv.y, yv.y, red[9]);
+                        red[10] = fma(cr.x, gn.x, red[10]); red[10] = fma(cr.y, gn.y, red[10]);
+                        red[11] = fma(cr.x, sv.x, red[11]); red[11] = fma(cr.y, sv.y, red[11]);
+                        red[12] = fma(cr.x, yv.x, red[12]); red[12] = fma(cr.y, yv.y, red[12]);
+                        red[13] = fma(cr.x, os.x, red[13]); red[13] = fma(cr.y, os.y, red[13]);
+                        red[14] = fma(cr.x, oy.x, red[14]); red[14] = fma(cr.y, oy.y, red[14]);
+                        rdot[0] = fma(r.x, gn.x, rdot[0]); rdot[0] = fma(r.y, gn.y, rdot[0]);
+                        rdot[1] = fma(r.x, sv.x, rdot[1]); rdot[1] = fma(r.y, sv.y, rdot[1]);
+                        rdot[2] = fma(r.x, yv.x, rdot[2]); rdot[2] = fma(r.y, yv.y, rdot[2]);
+                        rdot[3] = fma(r.x, os.x, rdot[3]); rdot[3] = fma(r.y, os.y, rdot[3]);
+                        rdot[4] = fma(r.x, oy.x, rdot[4]); rdot[4] = fma(r.y, oy.y, rdot[4]);
                     }
                     rsq = fma(r.x, r.x, rsq); rsq = fma(r.y, r.y, rsq);
                 }
             }
             rsq = group_sum<G>(rsq);
+            if (GRAM && rowdots != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) rdot[q] = group_sum<G>(rdot[q]);
+                if (live && lane == 0) {
+                    double *o = rowdots + (size_t)(row0 + rr) * 5;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) o[q] = rdot[q];
+                }
+            }
             if (live && lane == 0) {
                 const int cnt = scnt[rr];
                 if (cnt == 1) {

@@ -16,15 +16,12 @@ sys.path.insert(0, os.path.join(ROOT, "ltr-lowrank-sdp_b200"))
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    ("r1 kernels (register step, separate <D,T>)", {"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0"}),
-    ("bulk step, separate <D,T>", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "0"}),
-    ("bulk step, dot mode 1 (peeled diagonal, 8 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"}),
-    ("bulk step, dot mode 2 (last gathered row, 7 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "2"}),
-    ("bulk step, dot mode 3 (last gathered row, 6 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "3"}),
-    ("bulk step, dot mode 4 (peeled diagonal, 7 CTAs/SM)", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "4"}),
-    ("bulk step tile24 x4, separate <D,T>", {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "0", "LORADS_STEP_TILE": "24", "LORADS_STEP_STAGES": "4"}),
+    ("r1 kernels (register step, separate <D,T>, direction reads R and CR)", {"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0", "LORADS_ROWDOTS": "0"}),
+    ("bulk step, dot mode 3, direction reads R and CR", {"LORADS_ROWDOTS": "0"}),
+    ("default: bulk step, dot mode 3, direction from carried row products", {}),
+    ("default with separate <D,T>", {"LORADS_SPMM_DOT": "0"}),
 ]
-KEYS = ["LORADS_STEP_BULK", "LORADS_SPMM_DOT", "LORADS_STEP_TILE", "LORADS_STEP_STAGES", "LORADS_STEP_VARIANT"]
+KEYS = ["LORADS_STEP_BULK", "LORADS_SPMM_DOT", "LORADS_STEP_TILE", "LORADS_STEP_STAGES", "LORADS_STEP_VARIANT", "LORADS_ROWDOTS"]
 
 
 def main():

@@ -468,19 +468,21 @@ def _diag_problem_irregular_rows(lb, n, seed):
 @pytest.mark.parametrize("n,r", [(1500, 32), (4099, 12), (777, 70)])
 def test_step_and_product_kernel_variants_agree(lb, monkeypatch, n, r):
     """k_mc_step_bulk (bulk-copy pipeline: several tile sizes / ring depths, ragged last tile, rows with 0 / 1 / 3
-    constraints) and the <D, C D> epilogue of the sparse product against the register-staged step kernel with a separate
-    dot pass: same trajectory to rounding over 10 ALM inner iterations."""
+    constraints), the <D, C D> epilogue of the sparse product and the direction pass fed by carried row / <C R, .>
+    products (default) against the register-staged step kernel with a separate dot pass and a direction pass that reads
+    R and C R: same trajectory to rounding over 10 ALM inner iterations."""
     p = _diag_problem_irregular_rows(lb, n, r)
     rng = np.random.default_rng(n)
     R0 = rng.random((n, r)) - rng.random((n, r))
     rho = 1.0 / np.sqrt(n)
     settings = [{"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0"}, {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"},
+                {"LORADS_STEP_BULK": "1", "LORADS_ROWDOTS": "0"},
                 {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "16", "LORADS_STEP_STAGES": "4"},
                 {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "8", "LORADS_STEP_STAGES": "2"},
                 {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "40", "LORADS_STEP_STAGES": "3"}]
     outs = []
     for env in settings:
-        for k in ("LORADS_STEP_BULK", "LORADS_SPMM_DOT", "LORADS_STEP_TILE", "LORADS_STEP_STAGES"):
+        for k in ("LORADS_STEP_BULK", "LORADS_SPMM_DOT", "LORADS_STEP_TILE", "LORADS_STEP_STAGES", "LORADS_ROWDOTS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
