@@ -181,10 +181,10 @@ def algorithmic_bytes(cls, info, n, ld, m, share=1.0):
         return 8.0 * nnzF + 8.0 * nnzP + 4.0 * (n + 1) + 2 * F
     if cls == "k_mc_spmm":   # CSR (col + value) + every row of D once + T written (a partitioned rank reads all of D)
         return 12.0 * nnzF + 4.0 * (n * share + 1) + 8.0 * n * ld + F
-    if cls == "k_mc_step":   # reads R, D, CR, T, G, s_old, y_old ; writes R, CR, G, s_new, y_new ; m-vectors
-        return 12 * F + 56.0 * m
-    if cls == "k_mc_dir":    # direction pass: reads G, s0, y0, s1, y1, R, CR ; writes D, q1, q2
-        return 8 * F + 16.0 * m
+    if cls == "k_mc_step":   # reads R, D, CR, T, G, s_old, y_old ; writes R, CR, G, s_new, y_new ; m-vectors ; 5 row products
+        return 12 * F + 56.0 * m + 40.0 * n * share
+    if cls == "k_mc_dir":    # direction pass: reads G, s0, y0, s1, y1 and the 5 row products ; writes D, q1, q2 (R and C R are
+        return 6 * F + 16.0 * m + 40.0 * n * share   # no longer read: <R_i, D_i> and <C R, D> come from carried products)
     if cls == "k_wsum":
         return 12.0 * info["nnzA"] + 8.0 * m + 16.0 * nnzP
     if cls == "k_gather":
