@@ -1,7 +1,8 @@
-"""Worker for tests/test_partition_gloo.py (CPU, gloo, world_size 2): the host-side logic of the row-block partitioned
-path -- row ownership from the C ABI's lgpu_partition_rows, CSR slicing with global column ids, the all-gather of the
-direction's rows and the all-reduce of the scalar packs -- emulated in numpy and checked against the single-process
-oracle.  No GPU work happens here."""
+"""Worker for tests/test_partition_gloo.py (CPU, gloo, world_size 2): the host-side logic of the N > 1 paths -- row
+ownership from the C ABI's lgpu_partition_rows, CSR slicing with global column ids, the all-gather of the direction's
+rows and the all-reduce of the scalar packs, the addressing of the peer-memory halo PUT (dst_off), the rank-order scalar
+all-reduce, and the by-cone partition's owner map and m-vector sum -- emulated in numpy and checked against the
+single-process oracle.  No GPU work happens here."""
 import os
 import sys
 
@@ -83,6 +84,64 @@ def main():
     taus = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(taus, torch.tensor([tau], dtype=torch.float64))
     assert all(float(t[0]) == tau for t in taus)
+    # 4. halo PUT addressing (peer-memory exchange): every rank writes the rows its peers reference straight into THEIR halo
+    #    buffers at dst_off (derived locally, never communicated); emulated with an all-to-all of the packed rows.  What lands
+    #    in my halo must be, row for row, the global rows halo_gid names.
+    os.environ["LORADS_HALO"] = "1"
+    L = lb.cone_layout(p, 0, ["send_idx", "send_off", "send_cnt", "recv_off", "recv_cnt", "dst_off", "halo_gid"], world, rank)
+    halo = np.full((max(len(L["halo_gid"]), 1), r), np.nan)
+    for q_ in range(world):
+        if q_ == rank:
+            continue
+        s0, sc = int(L["send_off"][q_]), int(L["send_cnt"][q_])
+        rows = torch.from_numpy(np.ascontiguousarray(D[lo + L["send_idx"][s0:s0 + sc].astype(np.int64)]))
+        meta = torch.tensor([int(L["dst_off"][q_]), sc], dtype=torch.int64)
+        other_meta = torch.zeros(2, dtype=torch.int64)
+        # world 2: a symmetric exchange with the one peer
+        reqs = [dist.isend(meta, q_), dist.irecv(other_meta, q_)]
+        for rq in reqs:
+            rq.wait()
+        got = torch.zeros((int(other_meta[1]), r), dtype=torch.float64)
+        reqs = [dist.isend(rows, q_), dist.irecv(got, q_)]
+        for rq in reqs:
+            rq.wait()
+        off = int(other_meta[0])
+        assert off == int(L["recv_off"][q_]) and int(other_meta[1]) == int(L["recv_cnt"][q_])
+        halo[off:off + int(other_meta[1])] = got.numpy()
+    if len(L["halo_gid"]):
+        assert np.array_equal(halo[:len(L["halo_gid"])], D[L["halo_gid"].astype(np.int64)])
+    # 5. one-shot scalar all-reduce in RANK ORDER: every rank adds the same numbers in the same order -> same bits
+    mine = torch.tensor(np.random.default_rng(100 + rank).normal(size=18) * 1e8, dtype=torch.float64)
+    inbox = [torch.zeros(18, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(inbox, mine)
+    tot = np.zeros(18)
+    for src in range(world):
+        tot = tot + inbox[src].numpy()
+    allt = [torch.zeros(18, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allt, torch.from_numpy(tot))
+    assert all(np.array_equal(t.numpy(), tot) for t in allt)
+    # 6. by-cone partition of a multi-block problem: the owners' constraint values, summed over the ranks, are the whole
+    #    A(RR^T); gradient segments travel as "owner's value + zeros" and arrive bit for bit
+    qm = orc.read_sdpa(os.path.join(ROOT, "tests", "golden", "instances", "multiblock_lp.dat-s"))
+    cones = [orc.build_cone(bk, qm.m) for bk in qm.blocks]
+    cost = [float((c_.nnzP + len(c_.a_slot) + c_.n) * 8) for c_ in cones]
+    owner = lb.cone_owner_map(cost, world)
+    assert set(owner.tolist()) == set(range(world))
+    rngc = np.random.default_rng(5)
+    Rs = [rngc.normal(size=(c_.n, 4)) for c_ in cones]
+    whole = np.zeros(qm.m)
+    part = np.zeros(qm.m)
+    for k_, c_ in enumerate(cones):
+        cv = orc.cone_auv(c_, orc.uvt(c_, Rs[k_], Rs[k_]))
+        whole += cv
+        if owner[k_] == rank:
+            part += cv
+    tpart = torch.from_numpy(part.copy())
+    dist.all_reduce(tpart)
+    assert np.allclose(tpart.numpy(), whole, rtol=1e-13, atol=1e-13 * np.max(np.abs(whole)))
+    seg = torch.from_numpy(Rs[0].copy() if owner[0] == rank else np.zeros_like(Rs[0]))
+    dist.all_reduce(seg)
+    assert np.array_equal(seg.numpy(), Rs[0])
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
