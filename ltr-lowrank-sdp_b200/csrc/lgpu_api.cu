@@ -669,7 +669,7 @@ extern "C" int lgpu_create(lgpu_ctx **out, int device)
     ctx->device = device;
     if (const char *v = getenv("LORADS_STEP_VARIANT")) ctx->step_variant = atoi(v);
     if (const char *v = getenv("LORADS_FAST_FETCH")) ctx->fast_fetch = atoi(v) != 0;
-    if (const char *v = getenv("LORADS_ROWDOTS")) ctx->rowdots_enabled = atoi(v) != 0;
+    if (const char *v = getenv("LORADS_ROWDOTS")) { ctx->rowdots_enabled = atoi(v) != 0; ctx->rowdots_force = atoi(v) >= 2; }
     if (const char *v = getenv("LORADS_STEP_BULK")) ctx->step_bulk = atoi(v);
     if (const char *v = getenv("LORADS_FUSE_PUT")) ctx->fuse_put = atoi(v) != 0;
     if (const char *v = getenv("LORADS_STEP_TILE")) ctx->step_tile_rows = atoi(v);
@@ -1348,7 +1348,12 @@ static int layout_and_alloc(lgpu_ctx *ctx, const int64_t *rank, int lbfgs_len)
     if (ctx->mc) {
         TRY(alloc_flat(ctx, &ctx->CR));
         TRY(alloc_flat(ctx, &ctx->CD));
-        if (lbfgs_len == 2 && ctx->rowdots_enabled) TRY(dev_alloc(ctx, &ctx->rowdots, (size_t)ctx->cones[0].n_alloc * 5));
+        /* carried row products pay where the factor streams from DRAM; on L2-resident problems they only add five
+         * reductions and 40 bytes per row to a latency-bound pass (torus n = 2e4: step pass 23 -> 28 us), so they are kept for
+         * factors of 64 MB and more (LORADS_ROWDOTS=2 forces them on for tests) */
+        const bool big = (double)ctx->cones[0].n_alloc * (double)ctx->cones[0].ld * 8.0 >= 64.0e6;
+        if (lbfgs_len == 2 && ctx->rowdots_enabled && (big || ctx->rowdots_force))
+            TRY(dev_alloc(ctx, &ctx->rowdots, (size_t)ctx->cones[0].n_alloc * 5));
     }
     if (ctx->world > 1 && !ctx->cone_par) {
         dev_free(ctx->gfull); dev_free(ctx->halo); dev_free(ctx->sendbuf);
@@ -2342,40 +2347,38 @@ extern "C" int lgpu_alm_inner_update(lgpu_ctx *ctx, double rho, double tau, doub
         const int grid = (int)std::min<int64_t>(ntiles, ctx->num_sms);
         const int threads = LGPU_TPB + 32 * nstage;
         Prof pr(ctx, KC_MC_STEP);
-        if (gram) {
+#define MC_STEP_BULK(KERN, SP, ROWPTR)                                                                                              \
+    DISPATCH_G(G, {                                                                                                                   \
+        auto kern = KERN;                                                                                                             \
+        static size_t attr_bytes = 0;                                                                                                 \
+        if (bulk_smem > attr_bytes) {                                                                                                 \
+            CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));                         \
+            attr_bytes = bulk_smem;                                                                                                   \
+        }                                                                                                                             \
+        kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G, \
+                                                       ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs, \
+                                                       ctx->q1, ctx->q2, ctx->M1, gram ? ctx->s[jo] : nullptr,                        \
+                                                       gram ? ctx->y[jo] : nullptr, ctx->partials, ctx->counter, ctx->dsc, SP,         \
+                                                       SC_BETA0 + jn, ROWPTR);                                                        \
+    })
+        if (gram && ctx->rowdots != nullptr) {
             SlotSpec<15> sp;
             for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
             for (int k = 0; k < 5; ++k) sp.slot[10 + k] = SC_CRG + k;
             sp.accumulate = 0;
-            wrote_rowdots = ctx->rowdots != nullptr;
-            DISPATCH_G(G, {
-                auto kern = k_mc_step_bulk<GG, true>;
-                static size_t attr_bytes = 0;
-                if (bulk_smem > attr_bytes) {
-                    CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
-                    attr_bytes = bulk_smem;
-                }
-                kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
-                                                               ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
-                                                               ctx->q1, ctx->q2, ctx->M1, ctx->s[jo], ctx->y[jo], ctx->partials, ctx->counter,
-                                                               ctx->dsc, sp, SC_BETA0 + jn, ctx->rowdots);
-            });
+            wrote_rowdots = true;
+            MC_STEP_BULK((k_mc_step_bulk<GG, true, true>), sp, ctx->rowdots);
+        } else if (gram) {
+            SlotSpec<10> sp;
+            for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
+            sp.accumulate = 0;
+            MC_STEP_BULK((k_mc_step_bulk<GG, true, false>), sp, nullptr);
         } else {
             SlotSpec<3> sp;
             sp.slot[0] = SC_LAG; sp.slot[1] = SC_YS; sp.slot[2] = SC_PINF; sp.accumulate = 0;
-            DISPATCH_G(G, {
-                auto kern = k_mc_step_bulk<GG, false>;
-                static size_t attr_bytes = 0;
-                if (bulk_smem > attr_bytes) {
-                    CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
-                    attr_bytes = bulk_smem;
-                }
-                kern<<<grid, threads, bulk_smem, ctx->stream>>>(c.n, (int)c.ld, tr, nstage, tau, rho, ctx->R, ctx->U, ctx->CR, ctx->CD, ctx->G,
-                                                               ctx->s[jn], ctx->y[jn], c.rc_ptr, c.rc_gid, c.rc_a, ctx->lam, ctx->b, ctx->cvs,
-                                                               ctx->q1, ctx->q2, ctx->M1, nullptr, nullptr, ctx->partials, ctx->counter,
-                                                               ctx->dsc, sp, SC_BETA0 + jn, nullptr);
-            });
+            MC_STEP_BULK((k_mc_step_bulk<GG, false, false>), sp, nullptr);
         }
+#undef MC_STEP_BULK
     } else if (gram) {
         SlotSpec<10> sp;
         for (int k = 0; k < 10; ++k) sp.slot[k] = SC_LAG + k;
@@ -2977,6 +2980,46 @@ __global__ void __launch_bounds__(LGPU_TPB) k_basis_update(int64_t n, int k, con
     }
 }
 
+/* The same two kernels with the Lanczos step's own update fused in (w1 = w - alpha q_k is formed on the fly, with the same
+ * fma, instead of by a separate launch) and |w|^2 -- hence beta_k and 1 / beta_k, by `post` -- reduced by the update kernel
+ * itself: 4 launches per step instead of 6 on the latency-bound cones. */
+__global__ void __launch_bounds__(LGPU_TPB) k_basis_dots_fused(int64_t n, const double *__restrict__ Q, const double *__restrict__ w,
+                                                               const double *__restrict__ qk, const double *__restrict__ alpha_p,
+                                                               double *__restrict__ h)
+{
+    __shared__ double sh[LGPU_TPB / 32];
+    const double *q = Q + (size_t)blockIdx.x * n;
+    const double alpha = *alpha_p;
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += LGPU_TPB) a = fma(q[i], fma(-alpha, qk[i], w[i]), a);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < LGPU_TPB / 32; ++k) t += sh[k];
+        h[blockIdx.x] = t;
+    }
+}
+template <class P>
+__global__ void __launch_bounds__(LGPU_TPB) k_basis_update_fused(int64_t n, int k, const double *__restrict__ Q,
+                                                                 const double *__restrict__ h, double *__restrict__ w,
+                                                                 const double *__restrict__ qk, const double *__restrict__ alpha_p,
+                                                                 double *partials, unsigned int *counter, double *dsc, SlotSpec<1> spec,
+                                                                 P post)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double alpha = *alpha_p;
+    double red[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = fma(-alpha, qk[i], w[i]);
+        for (int j = 0; j < k; ++j) a = fma(-h[j], Q[(size_t)j * n + i], a);
+        w[i] = a;
+        red[0] = fma(a, a, red[0]);
+    }
+    grid_reduce_finish<1, P>(red, partials, counter, dsc, spec, post);
+}
+
 /* S q for the partitioned fused layout: this rank's rows of (C - Diag(sum_k lambda_k a_k)) q into w at their GLOBAL
  * positions; q is a replicated full-length vector.  Column ids are global (all-gather mode) or local/halo ids that
  * halo_gid maps back to global rows. */
@@ -3050,26 +3093,30 @@ static int lanczos_min_eig(lgpu_ctx *ctx, int64_t n, int64_t vec_len, const Lanc
         const double *qm = k > 0 ? qptr(k - 1) : nullptr;
         TRY(apply(qk, qm, k > 0 ? dbe + (k - 1) : nullptr, w));
         /* w -= alpha_k q_k ; then (small problems) against the whole basis ; beta_k = |w| */
-        launch_map(ctx, n, [=] __device__(int64_t i) { w[i] = fma(-dsc[SC_LANCZOS], qk[i], w[i]); });
+        double *ak = dal + k, *bk = dbe + k;
+        auto finish = [=] __device__(double *sc) {
+            const double b = sqrt(sc[SC_LANCZOS + 1]);
+            *ak = sc[SC_LANCZOS];
+            *bk = b;
+            sc[SC_LANCZOS + 3] = b > 0.0 ? 1.0 / b : 0.0; /* an exhausted Krylov space yields zeros, not NaNs */
+        };
         if (full) {
             {
                 Prof pr(ctx, KC_REDUCE);
-                k_basis_dots<<<k + 1, LGPU_TPB, 0, ctx->stream>>>(vec_len, Q, w, hbuf);
+                k_basis_dots_fused<<<k + 1, LGPU_TPB, 0, ctx->stream>>>(vec_len, Q, w, qk, dsc + SC_LANCZOS, hbuf);
             }
             {
                 Prof pr(ctx, KC_VEC);
-                k_basis_update<<<grid_for(ctx, n, (const void *)k_basis_update), LGPU_TPB, 0, ctx->stream>>>(vec_len, k + 1, Q, hbuf, w);
+                k_basis_update_fused<<<grid_for(ctx, n), LGPU_TPB, 0, ctx->stream>>>(vec_len, k + 1, Q, hbuf, w, qk, dsc + SC_LANCZOS,
+                                                                                    ctx->partials, ctx->counter, ctx->dsc,
+                                                                                    slot1(SC_LANCZOS + 1), finish);
             }
-        }
-        {
-            double *ak = dal + k, *bk = dbe + k;
-            launch_reduce_post<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) { acc[0] = fma(w[i], w[i], acc[0]); },
-                                  slot1(SC_LANCZOS + 1), [=] __device__(double *sc) {
-                                      const double b = sqrt(sc[SC_LANCZOS + 1]);
-                                      *ak = sc[SC_LANCZOS];
-                                      *bk = b;
-                                      sc[SC_LANCZOS + 3] = b > 0.0 ? 1.0 / b : 0.0; /* an exhausted Krylov space yields zeros, not NaNs */
-                                  });
+        } else {
+            launch_reduce_post<1>(ctx, n, [=] __device__(int64_t i, double(&acc)[1]) {
+                const double v = fma(-dsc[SC_LANCZOS], qk[i], w[i]);
+                w[i] = v;
+                acc[0] = fma(v, v, acc[0]);
+            }, slot1(SC_LANCZOS + 1), finish);
         }
         CHECK_LAUNCH(ctx);
         if (k + 1 < kmax) {

@@ -252,7 +252,7 @@ struct lgpu_ctx {
     /* per-row inner products <R_i, g_i>, <R_i, s_new_i>, <R_i, y_new_i>, <R_i, s_old_i>, <R_i, y_old_i> written by the bulk
      * step pass ([n_alloc][5]); with them and the carried <C R, .> the direction pass needs neither R nor C R */
     double *rowdots = nullptr;
-    bool rowdots_valid = false, rowdots_enabled = true;
+    bool rowdots_valid = false, rowdots_enabled = true, rowdots_force = false;
     double p1_host = 0.0; /* <C R, D> formed on the host from the carried products (added to dsc[SC_P1], which is then zero) */
     bool epi_done = false; /* q1, q2 and <C, R D^T> already produced by the direction pass for the current D */
     int h = 0, head = 0;

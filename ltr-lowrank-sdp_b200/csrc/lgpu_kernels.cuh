@@ -1338,7 +1338,7 @@ __host__ __device__ inline size_t step_bulk_stage_bytes(int nstream, int tr, int
     return (b + 127) / 128 * 128;
 }
 
-template <int G, bool GRAM>
+template <int G, bool GRAM, bool ROWD>
 __global__ void __launch_bounds__(LGPU_TPB + 32 * LGPU_STEP_MAX_STAGES, 1)
 k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, double *__restrict__ Rm, const double *__restrict__ D,
                double *__restrict__ CR, const double *__restrict__ T, double *__restrict__ Gd, double *__restrict__ sh,
@@ -1346,12 +1346,12 @@ k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, do
                const double *__restrict__ rca, const double *__restrict__ lam, const double *__restrict__ b,
                double *__restrict__ cvs, const double *__restrict__ q1, const double *__restrict__ q2, double *__restrict__ M1,
                const double *__restrict__ so, const double *__restrict__ yo, double *partials, unsigned int *counter, double *dsc,
-               SlotSpec<GRAM ? 15 : 3> spec, int beta_slot, double *__restrict__ rowdots)
+               SlotSpec<GRAM ? (ROWD ? 15 : 10) : 3> spec, int beta_slot, double *__restrict__ rowdots)
 {
-    /* GRAM: reductions [10..14] = <CR, g>, <CR, s_new>, <CR, y_new>, <CR, s_old>, <CR, y_old> and, per row, the same five
-     * partners against R_i into rowdots[i][0..4]: the next direction pass gets <R_i, D_i> and <C R, D> from them */
+    /* ROWD (with GRAM): reductions [10..14] = <CR, g>, <CR, s_new>, <CR, y_new>, <CR, s_old>, <CR, y_old> and, per row, the
+     * same five partners against R_i into rowdots[i][0..4]: the next direction pass gets <R_i, D_i> and <C R, D> from them */
     constexpr int NSTREAM = GRAM ? 7 : 5;
-    constexpr int NR = GRAM ? 15 : 3;
+    constexpr int NR = GRAM ? (ROWD ? 15 : 10) : 3;
     constexpr int NG = LGPU_TPB / G;
     extern __shared__ __align__(128) unsigned char smem[];
     const int ld2 = ld >> 1;
@@ -1489,6 +1489,10 @@ k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, do
                         red[7] = fma(os.x, yv.x, red[7]); red[7] = fma(os.y, yv.y, red[7]);
                         red[8] = fma(oy.x, yv.x, red[8]); red[8] = fma(oy.y, yv.y, red[8]);
                         red[9] = fma(yv.x, yv.x, red[9]); red[9] = fma(yv.y, yv.y, red[9]);
+                    }
+                    if (GRAM && ROWD) {
+                        const double2 os = sSo[ws];
+                        const double2 oy = sYo[ws];
                         red[10] = fma(cr.x, gn.x, red[10]); red[10] = fma(cr.y, gn.y, red[10]);
                         red[11] = fma(cr.x, sv.x, red[11]); red[11] = fma(cr.y, sv.y, red[11]);
                         red[12] = fma(cr.x, yv.x, red[12]); red[12] = fma(cr.y, yv.y, red[12]);
@@ -1504,7 +1508,7 @@ k_mc_step_bulk(int64_t n, int ld, int tr, int nstage, double tau, double rho, do
                 }
             }
             rsq = group_sum<G>(rsq);
-            if (GRAM && rowdots != nullptr) {
+            if (GRAM && ROWD) {
 #pragma unroll
                 for (int q = 0; q < 5; ++q) rdot[q] = group_sum<G>(rdot[q]);
                 if (live && lane == 0) {

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("world,graph,halo,peer", [
     (2, "random", "0", None), (2, "random", "1", None), (2, "random", "1", "0"), (2, "torus", None, None), (2, "torus", None, "0"),
     (4, "random", None, None), (4, "torus", None, None), (4, "torus", None, "0"), (8, "random", None, None), (8, "random", None, "0"),
-    (8, "torus", None, None), (2, "torus_relabelled", None, None), (4, "torus_relabelled", None, "0")])
+    (8, "torus", None, None), (2, "torus_relabelled", None, None), (4, "torus_relabelled", None, "0"),
+    (2, "random_rowdots", None, None)])
 def test_partitioned_run_matches_single_gpu(built, world, graph, halo, peer):
     """Row exchange: all-gather of every row (LORADS_HALO=0), the referenced rows only (=1), or the library's own choice
     (unset).  Transport: peer-memory PUT + one-shot scalar all-reduce from our own kernels (default) or NCCL
@@ -28,6 +29,12 @@ def test_partitioned_run_matches_single_gpu(built, world, graph, halo, peer):
         # scrambled vertex labels + forced breadth-first relabelling: partition, halos and PUT lists in the new labels,
         # factors in and out in the caller's order (scattered rows per rank)
         env["LORADS_REORDER"] = "1"
+    env.pop("LORADS_ROWDOTS", None)
+    if graph == "random_rowdots":
+        # the direction pass fed by carried row / <C R, .> products (default only for factors >= 64 MB) on a partitioned run:
+        # the 18-scalar pack goes through the one-shot peer all-reduce
+        env["LORADS_ROWDOTS"] = "2"
+        env["LORADS_TEST_GRAPH"] = "random"
     env.pop("LORADS_HALO", None)
     env.pop("LORADS_PEER", None)
     if halo is not None:

@@ -475,8 +475,8 @@ def test_step_and_product_kernel_variants_agree(lb, monkeypatch, n, r):
     rng = np.random.default_rng(n)
     R0 = rng.random((n, r)) - rng.random((n, r))
     rho = 1.0 / np.sqrt(n)
-    settings = [{"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0"}, {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"},
-                {"LORADS_STEP_BULK": "1", "LORADS_ROWDOTS": "0"},
+    settings = [{"LORADS_STEP_BULK": "0", "LORADS_SPMM_DOT": "0", "LORADS_ROWDOTS": "0"}, {"LORADS_STEP_BULK": "1", "LORADS_SPMM_DOT": "1"},
+                {"LORADS_STEP_BULK": "1", "LORADS_ROWDOTS": "2"},   # carried row products forced on (default only for factors >= 64 MB)
                 {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "16", "LORADS_STEP_STAGES": "4"},
                 {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "8", "LORADS_STEP_STAGES": "2"},
                 {"LORADS_STEP_BULK": "1", "LORADS_STEP_TILE": "40", "LORADS_STEP_STAGES": "3"}]
