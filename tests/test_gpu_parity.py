@@ -224,7 +224,8 @@ def test_alm_admm_sequence_vs_reference(lb, name, mode):
             assert np.array_equal(new[:, :r_old], old)
             seed = np.zeros((old.shape[0], dr))
             k = min(old.shape[0], dr)
-            seed[np.arange(k), np.arange(k)] = 1.0 / np.sqrt(k)
+            if k > 0:
+                seed[np.arange(k), np.arange(k)] = 1.0 / np.sqrt(k)
             assert np.array_equal(new[:, r_old:], seed)
     ctx.close()
 
