@@ -10,10 +10,11 @@
  *   --rankSchedule <json>   {"rank_schedule":[...], "schedule_length":N}  (benchmark.py:123-133)
  *   --nearStallFactor <f>   scales the ALM stall counter threshold that triggers a rank change
  *   --disableOracle         skip the per-iteration oracle-rank eigen-decomposition (reported as 0)
- * `--device <id>` to choose the GPU, and `--ranks <P>` for a row-block partitioned run on P GPUs of this node: the
- * driver forks P processes (one per GPU, devices id .. id+P-1) BEFORE anything touches CUDA, rank 0 creates the NCCL id
- * and hands it to the others through pipes, every rank runs the same state machine on the same reduced scalars, and
- * only rank 0 prints and writes the log / JSON.
+ * `--device <id>` to choose the GPU, and `--ranks <P>` for a partitioned run on P GPUs of this node (row blocks of one
+ * MaxCut-type cone, whole cones otherwise): the driver reads the file once, then forks P processes (one per GPU,
+ * devices id .. id+P-1) BEFORE anything touches CUDA, so the ranks share the parsed problem copy-on-write; rank 0
+ * creates the NCCL id and hands it to the others through pipes, every rank runs the same state machine on the same
+ * reduced scalars, and only rank 0 prints and writes the log / JSON.
  */
 #include <ctype.h>
 #include <getopt.h>
@@ -273,12 +274,39 @@ int lorads_b200_main(int argc, char **argv)
     }
     params.rhoCellingADMM = params.rhoMax * 200;
 
-    /* ---- fork the ranks of a partitioned run (no CUDA call has happened yet) --------------------------------*/
+    printf("-----------------------------------------------------------\n");
+    printf("  L         OOO      RRRR       A      DDDD       SSS \n");
+    printf("  L        O   O     R   R     A A     D   D     S    \n");
+    printf("  L        O   O     RRRR     AAAAA    D   D      SSS \n");
+    printf("  L        O   O     R  R     A   A    D   D         S\n");
+    printf("  LLLLL     OOO      R   R    A   A    DDDD       SSS \n");
+    printf("-----------------------------------------------------------\n");
+    print_input(&params);
+    signal(SIGINT, on_sigint);
+
+    lh_sdpa data;
+    memset(&data, 0, sizeof(data));
+    lh_solver SS;
+    lh_solver *S = &SS;
+    memset(S, 0, sizeof(*S));
+    int exit_code = 0;
+
+    const double timeStart = lh_time();
+    if (lh_read_sdpa(params.fname, &data, 0) != 0) return 0; /* the reference also exits with status 0 here */
+    printf("Reading SDPA file in %f seconds \n", lh_time() - timeStart);
+    if (getenv("LORADS_SAVE_BINARY") && params.rank == 0 && lh_write_sdpa_binary(getenv("LORADS_SAVE_BINARY"), &data) != 0)
+        fprintf(stderr, "lorads_b200: cannot write the binary image '%s'\n", getenv("LORADS_SAVE_BINARY"));
+    printf("nConstrs = %lld, sdp nBlks = %lld, lp Cols = %lld\n", (long long)data.m, (long long)data.nBlks,
+           (long long)data.nLpCols);
+
+    /* ---- fork the ranks of a partitioned run ------------------------------------------------------------------
+     * The file has been read ONCE, with all the cores; the ranks inherit the parsed problem copy-on-write.  No CUDA call
+     * has happened yet and the reader's threads have been joined, so the children start from a single-threaded image. */
     pid_t kids[64];
     int nkids = 0;
     if (params.ranks > 64) params.ranks = 64;
     if (params.ranks > 1) {
-        /* the ranks read and preprocess at the same time: the reader and the layout builder divide the cores by this */
+        /* the ranks preprocess at the same time: the layout builder divides the cores by this */
         char nr[16];
         snprintf(nr, sizeof(nr), "%d", params.ranks);
         setenv("LORADS_LOCAL_RANKS", nr, 0);
@@ -320,31 +348,6 @@ int lorads_b200_main(int argc, char **argv)
         }
         params.device += params.rank;
     }
-
-    printf("-----------------------------------------------------------\n");
-    printf("  L         OOO      RRRR       A      DDDD       SSS \n");
-    printf("  L        O   O     R   R     A A     D   D     S    \n");
-    printf("  L        O   O     RRRR     AAAAA    D   D      SSS \n");
-    printf("  L        O   O     R  R     A   A    D   D         S\n");
-    printf("  LLLLL     OOO      R   R    A   A    DDDD       SSS \n");
-    printf("-----------------------------------------------------------\n");
-    print_input(&params);
-    signal(SIGINT, on_sigint);
-
-    lh_sdpa data;
-    memset(&data, 0, sizeof(data));
-    lh_solver SS;
-    lh_solver *S = &SS;
-    memset(S, 0, sizeof(*S));
-    int exit_code = 0;
-
-    const double timeStart = lh_time();
-    if (lh_read_sdpa(params.fname, &data, 0) != 0) return 0; /* the reference also exits with status 0 here */
-    printf("Reading SDPA file in %f seconds \n", lh_time() - timeStart);
-    if (getenv("LORADS_SAVE_BINARY") && params.rank == 0 && lh_write_sdpa_binary(getenv("LORADS_SAVE_BINARY"), &data) != 0)
-        fprintf(stderr, "lorads_b200: cannot write the binary image '%s'\n", getenv("LORADS_SAVE_BINARY"));
-    printf("nConstrs = %lld, sdp nBlks = %lld, lp Cols = %lld\n", (long long)data.m, (long long)data.nBlks,
-           (long long)data.nLpCols);
 
     const double timeSolveStart = lh_time();
     if (params.rankScheduleFile) {
