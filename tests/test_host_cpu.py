@@ -210,6 +210,24 @@ def test_cli_surface_matches_reference_options(built, tmp_path):
     assert r.returncode == 3 and not (tmp_path / "o.json").exists()
 
 
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_ranks_are_forked_after_the_file_is_read(built, ranks):
+    """`--ranks P` (main.c): the file is read once, by the parent, and the ranks are forked afterwards; rank 0 alone prints.
+    Without a GPU every rank stops at the device with the no-fallback message, the parent reaps them and exits 3 -- no
+    rank is left waiting for the communicator id."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present: covered by the multi-GPU tests")
+    except Exception:
+        pass
+    r = built.run_solver([inst_path("G11"), "--ranks", str(ranks)], timeout=60)
+    assert r.returncode == 3
+    assert r.stdout.count("Reading SDPA file in") == 1 and r.stdout.count("Input parameters:") == 1
+    assert r.stdout.count("nConstrs = 800, sdp nBlks = 1, lp Cols = 0") == 1 and r.stdout.count("Pre-solver starts") == 1
+    assert r.stderr.count("no CPU fallback") == ranks
+
+
 def test_partition_and_classify_need_no_gpu(built):
     assert built.partition_rows(10_000_000, 8, 7) == (8_750_000, 10_000_000, 1_250_000)
     p = built.read_sdpa(inst_path("multiblock_lp"))
