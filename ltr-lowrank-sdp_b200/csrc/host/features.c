@@ -9,7 +9,11 @@
  *
  * Conventions of processor.py that are kept: all SDP blocks form ONE block-diagonal n x n matrix per constraint
  * (n = sum of block dimensions, block k starts at row offset[k]); the .dat-s stores one triangle, the extractor works on
- * the symmetrised matrix, so an off-diagonal entry counts twice; the LP block is not part of these statistics.
+ * the symmetrised matrix, so an off-diagonal entry counts twice; the LP block is not part of these statistics (the
+ * extractor keeps the positive block dimensions only, processor.py:75-76, and drops the entries of a trailing LP block).
+ * The reader negates the objective (lorads_file_io.c:317-319): column 0 of the parsed arrays holds -F0, the extractor
+ * works on the file's F0, so everything that depends on the sign of C (its trace, <A_i, C>) is handed over in the
+ * FILE's sign.
  */
 #include <math.h>
 #include <stdlib.h>
@@ -50,7 +54,7 @@ int lh_constraint_stats(const lh_sdpa *d, double *out, double *out_obj)
             for (int64_t e = e0; e < e1; ++e) {
                 int64_t i, j;
                 unpack_lower(nk, d->matIdx[k][e], &i, &j);
-                const double v = d->matElem[k][e], a = fabs(v);
+                const double v = c == 0 ? -d->matElem[k][e] : d->matElem[k][e], a = fabs(v); /* column 0 holds -F0 */
                 if (i == j) {
                     nnz += 1; fro2 += v * v; trace += v; diag2 += v * v;
                     if (rowsum[i] == 0.0) touched[nt++] = i;
@@ -120,4 +124,178 @@ int lh_constraint_rows(const lh_sdpa *d, int64_t *ptr, int64_t *rows, int64_t *c
     free(buf);
     *count = total;
     return 0;
+}
+
+/* ---- couplings: what the extractor's cost-alignment and edge features are made of ----------------------------------
+ * processor.py:347-366 takes <A_i, C> for every constraint, :497-505 the share of A_i's rows that C touches too;
+ * :580-600 multiplies the incidence pattern with its transpose (overlap = P P^T) and, for every pair with a common row,
+ * :640-643 / :691-693 takes <A_i, A_j>.  All of it follows from the parsed arrays: positions are matched on
+ * (block, packed index), an off-diagonal position counts twice (symmetrised matrices). */
+typedef struct { int64_t key, con; double val; } pos_entry;
+
+static int cmp_pos(const void *a, const void *b)
+{
+    const pos_entry *x = (const pos_entry *)a, *y = (const pos_entry *)b;
+    if (x->key != y->key) return (x->key > y->key) - (x->key < y->key);
+    return (x->con > y->con) - (x->con < y->con);
+}
+
+/* entries of the constraint columns [c0, c1] of all blocks, sorted by (position, constraint).  key = 2 * position +
+ * (1 if off-diagonal): the low bit carries the weight of the position (1 diagonal, 2 off-diagonal) */
+static pos_entry *sorted_positions(const lh_sdpa *d, int64_t c0, int64_t c1, int64_t *count)
+{
+    int64_t E = 0;
+    for (int64_t k = 0; k < d->nBlks; ++k) E += d->matBeg[k][c1 + 1] - d->matBeg[k][c0];
+    pos_entry *P = (pos_entry *)malloc(sizeof(pos_entry) * (size_t)(E > 0 ? E : 1));
+    if (!P) return NULL;
+    int64_t q = 0, base = 0;
+    for (int64_t k = 0; k < d->nBlks; ++k) {
+        const int64_t nk = d->blkDims[k];
+        for (int64_t c = c0; c <= c1; ++c)
+            for (int64_t e = d->matBeg[k][c]; e < d->matBeg[k][c + 1]; ++e) {
+                int64_t i, j;
+                unpack_lower(nk, d->matIdx[k][e], &i, &j);
+                P[q].key = 2 * (base + d->matIdx[k][e]) + (i != j);
+                P[q].con = c;
+                P[q].val = d->matElem[k][e];
+                ++q;
+            }
+        base += nk * (nk + 1) / 2;
+    }
+    qsort(P, (size_t)E, sizeof(pos_entry), cmp_pos);
+    *count = E;
+    return P;
+}
+
+/* inner[i] = <A_i, F0> (the cost matrix as the file states it), rows_shared[i] = |rows(A_i) & rows(F0)| (either may be
+ * NULL), i = 0 .. m-1 */
+int lh_constraint_cost_alignment(const lh_sdpa *d, double *inner, int64_t *rows_shared)
+{
+    if (!d) return 1;
+    const int64_t m = d->m, nb = d->nBlks;
+    if (inner) {
+        int64_t nc = 0;
+        pos_entry *C = sorted_positions(d, 0, 0, &nc);
+        if (!C) return 1;
+        int64_t base = 0;
+        for (int64_t i = 0; i < m; ++i) inner[i] = 0.0;
+        for (int64_t k = 0; k < nb; ++k) {
+            const int64_t nk = d->blkDims[k];
+            for (int64_t c = 1; c <= m; ++c)
+                for (int64_t e = d->matBeg[k][c]; e < d->matBeg[k][c + 1]; ++e) {
+                    int64_t i, j;
+                    unpack_lower(nk, d->matIdx[k][e], &i, &j);
+                    const int64_t key = 2 * (base + d->matIdx[k][e]) + (i != j);
+                    int64_t lo = 0, hi = nc; /* first entry of C at this position (duplicates in the file add up) */
+                    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (C[mid].key < key) lo = mid + 1; else hi = mid; }
+                    for (; lo < nc && C[lo].key == key; ++lo) inner[c - 1] -= (i != j ? 2.0 : 1.0) * d->matElem[k][e] * C[lo].val; /* -: the file's F0 */
+                }
+            base += nk * (nk + 1) / 2;
+        }
+        free(C);
+    }
+    if (rows_shared) {
+        int64_t n = 0;
+        for (int64_t k = 0; k < nb; ++k) n += d->blkDims[k];
+        unsigned char *mark = (unsigned char *)calloc((size_t)(n > 0 ? n : 1), 1);
+        int64_t *ptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+        int64_t cnt = 0, off = 0;
+        if (!mark || !ptr || lh_constraint_rows(d, ptr, NULL, &cnt) != 0) { free(mark); free(ptr); return 1; }
+        int64_t *rows = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt > 0 ? cnt : 1));
+        if (!rows || lh_constraint_rows(d, ptr, rows, &cnt) != 0) { free(mark); free(ptr); free(rows); return 1; }
+        for (int64_t k = 0; k < nb; ++k) {
+            for (int64_t e = d->matBeg[k][0]; e < d->matBeg[k][1]; ++e) {
+                int64_t i, j;
+                unpack_lower(d->blkDims[k], d->matIdx[k][e], &i, &j);
+                mark[off + i] = 1;
+                mark[off + j] = 1;
+            }
+            off += d->blkDims[k];
+        }
+        for (int64_t c = 0; c < m; ++c) {
+            int64_t s = 0;
+            for (int64_t t = ptr[c]; t < ptr[c + 1]; ++t) s += mark[rows[t]];
+            rows_shared[c] = s;
+        }
+        free(mark); free(ptr); free(rows);
+    }
+    return 0;
+}
+
+/* The pairs i < j of constraints with a common row (the non-zeros of P P^T above its diagonal) as a CSR over i:
+ * ptr[m + 1], col = j ascending, overlap = |rows(A_i) & rows(A_j)|, inner = <A_i, A_j>.  Call with col == NULL to size
+ * (fills ptr and *count only). */
+int lh_constraint_pairs(const lh_sdpa *d, int64_t *ptr, int64_t *col, int64_t *overlap, double *inner, int64_t *count)
+{
+    if (!d || !ptr || !count) return 1;
+    const int64_t m = d->m, nb = d->nBlks;
+    int64_t n = 0, nrows = 0;
+    for (int64_t k = 0; k < nb; ++k) n += d->blkDims[k];
+    int rc = 1;
+    int64_t *cptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m + 1));
+    int64_t *crow = NULL, *rptr = NULL, *rcon = NULL, *cur = NULL, *acc = NULL, *touched = NULL;
+    pos_entry *P = NULL;
+    if (!cptr || lh_constraint_rows(d, cptr, NULL, &nrows) != 0) goto done;
+    crow = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nrows > 0 ? nrows : 1));
+    rptr = (int64_t *)calloc((size_t)(n + 2), sizeof(int64_t));
+    rcon = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nrows > 0 ? nrows : 1));
+    cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    acc = (int64_t *)calloc((size_t)(m > 0 ? m : 1), sizeof(int64_t));
+    touched = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m > 0 ? m : 1));
+    if (!crow || !rptr || !rcon || !cur || !acc || !touched || lh_constraint_rows(d, cptr, crow, &nrows) != 0) goto done;
+    /* row -> constraints, ascending constraint ids */
+    for (int64_t t = 0; t < nrows; ++t) rptr[crow[t] + 1]++;
+    for (int64_t r = 0; r < n; ++r) rptr[r + 1] += rptr[r];
+    for (int64_t r = 0; r < n; ++r) cur[r] = rptr[r];
+    for (int64_t c = 0; c < m; ++c)
+        for (int64_t t = cptr[c]; t < cptr[c + 1]; ++t) rcon[cur[crow[t]]++] = c;
+    /* overlap counts: constraint i meets, through each of its rows, the later constraints on that row.  The cursor of a
+     * row only moves forward (i ascends), so every incidence is skipped once */
+    for (int64_t r = 0; r < n; ++r) cur[r] = rptr[r];
+    int64_t total = 0;
+    ptr[0] = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        int64_t nt = 0;
+        for (int64_t t = cptr[i]; t < cptr[i + 1]; ++t) {
+            const int64_t r = crow[t];
+            while (cur[r] < rptr[r + 1] && rcon[cur[r]] <= i) ++cur[r];
+            for (int64_t q = cur[r]; q < rptr[r + 1]; ++q) {
+                const int64_t j = rcon[q];
+                if (acc[j]++ == 0) touched[nt++] = j;
+            }
+        }
+        qsort(touched, (size_t)nt, sizeof(int64_t), cmp_i64);
+        for (int64_t t = 0; t < nt; ++t) {
+            if (col) { col[total + t] = touched[t]; if (overlap) overlap[total + t] = acc[touched[t]]; if (inner) inner[total + t] = 0.0; }
+            acc[touched[t]] = 0;
+        }
+        total += nt;
+        ptr[i + 1] = total;
+    }
+    *count = total;
+    if (col && inner && total > 0) {
+        /* <A_i, A_j>: the constraints that share a POSITION meet in that position's group; a pair with a common position has
+         * a common row, so it is in the CSR */
+        int64_t E = 0;
+        P = sorted_positions(d, 1, m, &E);
+        if (!P) goto done;
+        for (int64_t g0 = 0; g0 < E;) {
+            int64_t g1 = g0 + 1;
+            while (g1 < E && P[g1].key == P[g0].key) ++g1;
+            const double w = (P[g0].key & 1) ? 2.0 : 1.0;
+            for (int64_t a = g0; a < g1; ++a)
+                for (int64_t b2 = a + 1; b2 < g1; ++b2) {
+                    const int64_t i = P[a].con - 1, j = P[b2].con - 1;
+                    if (i == j) continue; /* a position listed twice for one constraint */
+                    int64_t lo = ptr[i], hi = ptr[i + 1];
+                    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (col[mid] < j) lo = mid + 1; else hi = mid; }
+                    if (lo < ptr[i + 1] && col[lo] == j) inner[lo] += w * P[a].val * P[b2].val;
+                }
+            g0 = g1;
+        }
+    }
+    rc = 0;
+done:
+    free(cptr); free(crow); free(rptr); free(rcon); free(cur); free(acc); free(touched); free(P);
+    return rc;
 }

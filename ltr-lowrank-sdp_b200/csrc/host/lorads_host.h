@@ -72,6 +72,10 @@ void lh_free_sdpa(lh_sdpa *d);
 /* features.c: hand-off to the reference's feature extractor (dataset/processor.py:246-345) from the parsed arrays */
 int lh_constraint_stats(const lh_sdpa *d, double *out /* m x 7 */, double *out_obj /* 7, or NULL */);
 int lh_constraint_rows(const lh_sdpa *d, int64_t *ptr /* m + 1 */, int64_t *rows /* or NULL to size */, int64_t *count);
+/* couplings (processor.py:347-366, :497-505, :580-600, :640-643): <A_i, C>, rows shared with C; pairs i < j with a common row */
+int lh_constraint_cost_alignment(const lh_sdpa *d, double *inner /* m, or NULL */, int64_t *rows_shared /* m, or NULL */);
+int lh_constraint_pairs(const lh_sdpa *d, int64_t *ptr /* m + 1 */, int64_t *col /* or NULL to size */, int64_t *overlap,
+                        double *inner, int64_t *count);
 
 /* ---- phase states (reference: lorads_alm_state / lorads_admm_state, def_lorads_solver.h:198-238) */
 typedef struct {

@@ -359,6 +359,34 @@ def constraint_stats(p: SdpaProblem):
     return out, obj, ptr, rows[:cnt.value]
 
 
+def constraint_couplings(p: SdpaProblem) -> dict:
+    """Second half of the hand-off (dataset/processor.py:347-366, :497-505, :580-600, :640-643): `cost_inner` = <A_i, C> and
+    `rows_shared_with_cost` per constraint; the pairs i < j of constraints with a common row as a CSR (`ptr`, `col`) with
+    `overlap` = |rows_i & rows_j| and `inner` = <A_i, A_j>.  Host code, no GPU."""
+    H = host_lib()
+    H.lh_constraint_cost_alignment.restype = ctypes.c_int
+    H.lh_constraint_cost_alignment.argtypes = [ctypes.POINTER(_Sdpa), _c_dp, _c_lp]
+    H.lh_constraint_pairs.restype = ctypes.c_int
+    H.lh_constraint_pairs.argtypes = [ctypes.POINTER(_Sdpa), _c_lp, _c_lp, _c_lp, _c_dp, ctypes.POINTER(ctypes.c_int64)]
+    s, keep = _as_sdpa(p)
+    cost_inner = np.zeros(p.m)
+    shared = np.zeros(p.m, dtype=np.int64)
+    if H.lh_constraint_cost_alignment(ctypes.byref(s), cost_inner.ctypes.data_as(_c_dp), _i64(shared)) != 0:
+        raise LoradsError("lh_constraint_cost_alignment failed")
+    ptr = np.zeros(p.m + 1, dtype=np.int64)
+    cnt = ctypes.c_int64()
+    if H.lh_constraint_pairs(ctypes.byref(s), _i64(ptr), None, None, None, ctypes.byref(cnt)) != 0:
+        raise LoradsError("lh_constraint_pairs failed")
+    col = np.zeros(max(cnt.value, 1), dtype=np.int64)
+    ov = np.zeros(max(cnt.value, 1), dtype=np.int64)
+    inner = np.zeros(max(cnt.value, 1))
+    if H.lh_constraint_pairs(ctypes.byref(s), _i64(ptr), _i64(col), _i64(ov), inner.ctypes.data_as(_c_dp), ctypes.byref(cnt)) != 0:
+        raise LoradsError("lh_constraint_pairs failed")
+    del keep
+    k = cnt.value
+    return {"cost_inner": cost_inner, "rows_shared_with_cost": shared, "ptr": ptr, "col": col[:k], "overlap": ov[:k], "inner": inner[:k]}
+
+
 def run_solver(argv: Sequence[str], **kw) -> subprocess.CompletedProcess:
     """Run the drop-in binary exactly as benchmark.py runs the reference's (benchmark.py:240-262)."""
     if not os.path.exists(BINARY_PATH):

@@ -485,7 +485,7 @@ def test_constraint_stats_match_the_feature_extractor_formulas(built, name):
         return sp.csr_matrix((np.concatenate(vv), (np.concatenate(ri), np.concatenate(ci))), shape=(n, n))
 
     for c in list(range(0, p.m + 1, max(1, p.m // 40))) + [p.m]:
-        A = matrix(c)
+        A = matrix(c) if c else -matrix(0)           # the parsed objective is -F0; the hand-off is in the file's sign
         got = obj if c == 0 else stats[c - 1]
         diag = A.diagonal()
         row_sums = np.abs(A).sum(axis=1).A1
@@ -496,3 +496,146 @@ def test_constraint_stats_match_the_feature_extractor_formulas(built, name):
         assert got[6] == blocks
         if c > 0:
             assert np.array_equal(rows[ptr[c - 1]:ptr[c]], ur)
+
+
+FEATURE_FIXTURES = ["theta_n30", "multiblock_lp", "multiblock_sdp", "control_like_12_6", "general_sparse_n60", "dense_constraint_n24",
+                    "maxcut_torus_8x10", "G11"]
+
+
+@pytest.mark.parametrize("name", FEATURE_FIXTURES)
+def test_feature_handoff_reproduces_the_reference_extractor(built, name):
+    """SURVEY 8f-4 against the REFERENCE's own output: tests/golden/features.npz holds what dataset/processor.py
+    (SDPAParser + FeatureExtractor, run unmodified by tests/golden/make_feature_golden.py) produces for the fixture.  The
+    17 global, 16 node and 5 edge features are assembled here from nothing but the hand-off arrays (lh_constraint_stats,
+    lh_constraint_rows, lh_constraint_cost_alignment, lh_constraint_pairs) with the extractor's closed-form expressions
+    (processor.py:296-316, :368-505, :666-700); float64 internals to 1e-12, the float32 features to float32 rounding."""
+    lb = built
+    G = np.load(os.path.join(ROOT, "tests", "golden", "features.npz"))
+    g = lambda k: G[name + "/" + k]
+    p = lb.read_sdpa(inst_path(name))
+    stats, obj, ptr, rows = lb.constraint_stats(p)
+    cp = lb.constraint_couplings(p)
+    m, n, eps = p.m, int(np.sum(p.dims)), 1e-8
+    assert n == int(g("n"))
+    norms, nnz, traces, dnorm, gersh, rsz, blk = (stats[:, k] for k in range(7))
+    for ours, key in ((norms, "norms"), (nnz, "nnz_counts"), (traces, "traces"), (dnorm, "diag_norms"), (gersh, "gershgorin_bounds"),
+                      (blk, "blocks_touched"), (rsz, "row_sizes")):
+        assert np.allclose(ours, g(key), rtol=1e-12, atol=1e-12), key
+    c_fro = obj[0] if obj[1] > 0 else eps
+    assert np.isclose(c_fro, float(g("C_frob")), rtol=1e-13)
+    cos = np.where(nnz > 0, cp["cost_inner"] / (norms * c_fro + eps), 0.0) if obj[1] > 0 else np.zeros(m)
+    assert np.allclose(cos, g("cos_with_C"), rtol=1e-12, atol=1e-13)
+
+    # edges: every pair with a common row whose Jaccard index reaches the threshold (processor.py:666-712, m < 1000)
+    log_norms, log_nnz = np.log(1.0 + norms), np.log(1.0 + nnz)
+    pi = np.repeat(np.arange(m), np.diff(cp["ptr"]))
+    pj, ov = cp["col"], cp["overlap"].astype(np.float64)
+    jac = ov / (rsz[pi] + rsz[pj] - ov)
+    keep = jac >= 0.05
+    pi, pj, ov, jac, inner = pi[keep], pj[keep], ov[keep], jac[keep], cp["inner"][keep]
+    want_ei, want_ea = g("edge_index"), g("edge_attr")
+    if len(pi):
+        feat = np.stack([jac, ov / (np.minimum(rsz[pi], rsz[pj]) + eps), np.abs(inner) / (norms[pi] * norms[pj] + eps),
+                         np.minimum(log_norms[pi], log_norms[pj]), np.abs(log_norms[pi] - log_norms[pj])], axis=1)
+        ei = np.stack([np.stack([pi, pj]), np.stack([pj, pi])], axis=2).reshape(2, -1)     # (i, j), (j, i), pair after pair
+        assert np.array_equal(ei, want_ei)
+        assert np.allclose(np.repeat(feat, 2, axis=0).astype(np.float32), want_ea, rtol=2e-6, atol=1e-7)
+    else:
+        # no two constraints share a row (MaxCut): the extractor falls back to nearest neighbours in log-norm, which needs
+        # nothing from the problem data; its marker is a zero coupling column
+        assert len(cp["col"]) == 0 and np.all(want_ea[:, 2] == 0.0)
+        ei = want_ei
+    deg = np.bincount(ei[0], minlength=m) if ei.shape[1] else np.zeros(m)
+
+    # node features (processor.py:440-505)
+    x = np.zeros((m, 16))
+    nrhs = np.clip(p.b / (norms + eps), -100.0, 100.0)
+    x[:, 0], x[:, 1] = log_norms, log_nnz
+    x[:, 2] = np.clip(traces / (norms + eps), -100.0, 100.0)
+    x[:, 3] = dnorm / (norms + eps)
+    x[:, 4] = nrhs
+    x[:, 5] = np.log(1.0 + gersh)
+    x[:, 6] = cos
+    x[:, 7] = np.where(cos > 0.01, 1.0, np.where(cos < -0.01, -1.0, 0.0))
+    x[:, 8] = (log_norms - log_norms.mean()) / (log_norms.std() + eps)
+    x[:, 9] = (log_nnz - log_nnz.mean()) / (log_nnz.std() + eps)
+    x[:, 10] = (np.abs(nrhs) - np.abs(nrhs).mean()) / (np.abs(nrhs).std() + eps)
+    x[:, 11] = np.digitize(log_norms, np.percentile(log_norms, [25, 50, 75])) / 3.0
+    x[:, 12] = np.log(1.0 + rsz)
+    if obj[1] > 0:
+        x[:, 13] = np.where(rsz > 0, cp["rows_shared_with_cost"] / np.maximum(rsz, 1), 0.0)
+    x[:, 14] = np.log(1.0 + deg) if ei.shape[1] else 0.0
+    x[:, 15] = np.log(1.0 + blk)
+    want_x = g("node")
+    for k in range(16):
+        assert np.allclose(x[:, k].astype(np.float32), want_x[:, k], rtol=3e-6, atol=2e-6), (k, x[:3, k], want_x[:3, k])
+
+    # global features (processor.py:368-437 + the degree summary of :803-808)
+    nsq = float(n * n) + eps
+    dens = nnz / nsq
+    glob = [np.log(1.0 + n), np.log(1.0 + m), np.log(1.0 + n / max(m, 1)), np.log(1.0 + c_fro), np.log(1.0 + norms.mean()),
+            dens.mean(), dens.var(), obj[1] / nsq, log_norms.mean(), log_norms.std(), np.median(log_norms),
+            cos.mean(), cos.std(), cos.max(), cos.min(), deg.mean() if ei.shape[1] else 0.0, deg.std() if ei.shape[1] else 0.0]
+    assert np.allclose(np.array(glob, dtype=np.float32), g("global"), rtol=3e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_constraint_pairs_against_scipy_on_random_blocks(built, seed):
+    """lh_constraint_pairs / lh_constraint_cost_alignment on a random three-block problem with m > 1000 (the size at which
+    the extractor switches to `pattern @ pattern.T`, processor.py:563-583): overlap counts = the strict upper triangle of
+    P P^T, inner = sum(A_i .* A_j), cost terms = sum(A_i .* F0) -- including empty constraints, a position listed twice in
+    one constraint, and constraints that share a row but no position."""
+    import scipy.sparse as sp
+    lb = built
+    rng = np.random.default_rng(seed)
+    dims, m = [17, 40, 9], 1100
+    offs = np.concatenate([[0], np.cumsum(dims)])
+    n = int(offs[-1])
+    begs, idxs, vals = [], [], []
+    A = [sp.lil_matrix((n, n)) for _ in range(m + 1)]
+    for k, nk in enumerate(dims):
+        tri = nk * (nk + 1) // 2
+        ci, cv = [], []
+        for c in range(m + 1):
+            cnt = 0 if c % 7 == 3 else int(rng.integers(0, 4)) + (6 if c == 0 else 0)
+            ii = np.sort(rng.choice(tri, size=min(cnt, tri), replace=False))
+            if c % 11 == 5 and len(ii):
+                ii = np.sort(np.concatenate([ii, ii[:1]]))          # the same position twice: the values add up
+            vv = rng.normal(size=len(ii))
+            ci.append(ii)
+            cv.append(vv)
+            for t, v in zip(ii, vv):
+                j = int(np.floor(((2 * nk + 1) - np.sqrt((2.0 * nk + 1) ** 2 - 8.0 * t)) / 2.0))
+                while j * (2 * nk - j + 1) // 2 > t:
+                    j -= 1
+                while (j + 1) * (2 * nk - j) // 2 <= t:
+                    j += 1
+                i = int(t - j * (2 * nk - j + 1) // 2 + j)
+                A[c][offs[k] + i, offs[k] + j] += v
+                if i != j:
+                    A[c][offs[k] + j, offs[k] + i] += v
+        begs.append(np.concatenate([[0], np.cumsum([len(a) for a in ci])]))
+        idxs.append(np.concatenate(ci))
+        vals.append(np.concatenate(cv))
+    p = lb.SdpaProblem(m, dims, rng.normal(size=m), begs, idxs, vals)
+    cp = lb.constraint_couplings(p)
+    A = [a.tocsr() for a in A]
+    F0 = -A[0]                                                       # column 0 of the parsed arrays is -F0
+    rows = [np.unique(a.tocoo().row) for a in A]
+    # a position listed twice may cancel to an explicit zero only with probability 0; the row sets are those of the entries
+    P = sp.lil_matrix((m, n))
+    for c in range(1, m + 1):
+        P[c - 1, rows[c]] = 1
+    P = P.tocsr()
+    O = sp.triu(P @ P.T, k=1).tocsr()
+    O.sort_indices()
+    assert np.array_equal(cp["ptr"], O.indptr) and np.array_equal(cp["col"], O.indices)
+    assert np.array_equal(cp["overlap"], O.data.astype(np.int64))
+    pi = np.repeat(np.arange(m), np.diff(cp["ptr"]))
+    pick = rng.choice(len(pi), size=min(len(pi), 4000), replace=False)
+    want = np.array([A[pi[t] + 1].multiply(A[cp["col"][t] + 1]).sum() for t in pick])
+    assert np.allclose(cp["inner"][pick], want, rtol=1e-12, atol=1e-13)
+    assert np.count_nonzero(want) > 0 and np.count_nonzero(want == 0) > 0     # both kinds of pair are present
+    assert np.allclose(cp["cost_inner"], [A[c].multiply(F0).sum() for c in range(1, m + 1)], rtol=1e-12, atol=1e-13)
+    rc = set(rows[0].tolist())
+    assert np.array_equal(cp["rows_shared_with_cost"], [len(rc & set(rows[c].tolist())) for c in range(1, m + 1)])
